@@ -1,0 +1,269 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI
+(include/mgb200.h via ctypes) or through the host C layer that mirrors the reference's solver.h; the CPU oracle
+(oracle/) is only the checker.
+
+Bars (BASELINE.json north_star): assembled operators bit-exact; vectors produced by the Jacobi / red-black /
+transfer kernels bit-exact against the oracle on the same inputs (the kernels keep PETSc's operation order and
+never fuse multiply-add); norms, dots and residual histories within 1e-10 relative (tolerance written at each
+assert; the reductions use a different, deterministic summation order); iteration counts equal.
+"""
+import hashlib
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+mgb = importlib.import_module("multigrid-petsc_b200")
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+GOLD_U = np.load(os.path.join(HERE, "golden", "golden_u.npz"))
+RTOL = 1e-10          # north_star: residual norms and solution within 1e-10 relative in fp64
+
+JAC = "-pc_type jacobi -ksp_richardson_scale 0.8"
+
+
+def base(npts, levels, cycle=0, mesh=0, it=1000, v="3,3", mp=2):
+    return (f"-npts {npts} -mesh {mesh} -iter {it} -grids {levels} -levels {levels} "
+            f"-cycle {cycle} -map {mp} -v {v} -moreNorm 0")
+
+
+def _hex(v):
+    return np.array([float.fromhex(x) for x in v])
+
+
+# ------------------------------------------------------------------ assembled operators: bit-exact
+@pytest.mark.parametrize("npts,levels,mesh", [(5, 1, 0), (9, 2, 0), (17, 2, 0), (33, 4, 0), (101, 3, 0), (129, 4, 0),
+                                              (129, 7, 0), (65, 4, 1), (65, 4, 2), (257, 5, 0)])
+def test_csr_bit_exact(npts, levels, mesh):
+    opts = base(npts, levels, mesh=mesh) + " " + JAC
+    o = Oracle(opts)
+    s = mgb.Session(opts)
+    try:
+        for l in range(levels):
+            for which in (mgb.MAT_A, mgb.MAT_RES, mgb.MAT_PRO):
+                if which != mgb.MAT_A and l == levels - 1:
+                    continue
+                shape_o, ia_o, ja_o, va_o = o.csr(which, l)
+                shape_g, ia_g, ja_g, va_g = s.engine.csr(which, l)
+                assert shape_o == shape_g
+                assert np.array_equal(ia_o, ia_g), (which, l)
+                assert np.array_equal(ja_o, ja_g), (which, l)
+                assert va_o.tobytes() == va_g.tobytes(), (which, l)      # bit for bit
+    finally:
+        s.close()
+        o.close()
+
+
+def test_rhs_bit_exact_and_csr_spmv_matches_matrix_free():
+    opts = base(129, 4) + " " + JAC
+    o = Oracle(opts)
+    s = mgb.Session(opts)
+    e = s.engine
+    try:
+        b_o = o.to_grid(0, o.vec(0, 0))
+        assert b_o.tobytes() == e.get_vec(mgb.VEC_B, 0).tobytes()
+        rng = np.random.default_rng(0)
+        for l in range(4):
+            ni, nj = e.dims(l)
+            x = rng.uniform(-1, 1, (ni, nj))
+            e.set_vec(mgb.VEC_U, l, x)
+            e.apply(l, mgb.VEC_U, mgb.VEC_R)
+            y_mf = e.get_vec(mgb.VEC_R, l)
+            y_csr = e.csr_spmv(mgb.MAT_A, l, x.reshape(-1)).reshape(ni, nj)
+            y_o = o.matmult(0, l, x.reshape(-1)).reshape(ni, nj)
+            assert y_mf.tobytes() == y_o.tobytes()
+            assert y_csr.tobytes() == y_o.tobytes()
+    finally:
+        s.close()
+        o.close()
+
+
+# ------------------------------------------------------------------ single kernels vs the oracle, random inputs
+@pytest.mark.parametrize("npts,levels,mesh", [(17, 2, 0), (129, 4, 0), (101, 3, 0), (65, 4, 1), (65, 4, 2), (513, 5, 0)])
+def test_kernels_bit_exact_vs_oracle(npts, levels, mesh):
+    opts = base(npts, levels, mesh=mesh) + " " + JAC
+    o = Oracle(opts)
+    s = mgb.Session(opts)
+    e = s.engine
+    rng = np.random.default_rng(npts + mesh)
+    try:
+        for l in range(levels):
+            ni, nj = e.dims(l)
+            x = rng.uniform(-1, 1, (ni, nj))
+            b = rng.uniform(-1, 1, (ni, nj))
+            e.set_vec(mgb.VEC_U, l, x)
+            e.set_vec(mgb.VEC_B, l, b)
+            # residual r = b - A x
+            e.residual(l)
+            r_g = e.get_vec(mgb.VEC_R, l)
+            r_o = o.residual(l, b.reshape(-1), x.reshape(-1)).reshape(ni, nj)
+            assert r_g.tobytes() == r_o.tobytes()
+            rn = e.residual_norm(l)
+            assert rn == pytest.approx(o.norm2(r_o), rel=1e-13)
+            assert e.norm2(mgb.VEC_B, l) == pytest.approx(o.norm2(b), rel=1e-13)
+            assert e.dot(mgb.VEC_B, mgb.VEC_U, l) == pytest.approx(o.dot(b, x), rel=1e-10, abs=1e-12)
+            # Jacobi smoother: nonzero and zero guess, 1..3 sweeps
+            for nu, gz in ((1, False), (3, False), (2, False), (3, True), (1, True)):
+                e.set_vec(mgb.VEC_U, l, x)
+                e.smooth(l, mgb.jacobi(0.8), nu, gz)
+                x_g = e.get_vec(mgb.VEC_U, l)
+                x_o = o.smooth(l, b.reshape(-1), x.reshape(-1), nu, gz).reshape(ni, nj)
+                assert x_g.tobytes() == x_o.tobytes(), (l, nu, gz)
+            if l + 1 < levels:
+                nci, ncj = e.dims(l + 1)
+                # restriction, fused with the residual and from a stored residual
+                e.set_vec(mgb.VEC_U, l, x)
+                bc_o = o.matmult(1, l, r_o.reshape(-1)).reshape(nci, ncj)
+                e.restrict(l, fused=True)
+                assert e.get_vec(mgb.VEC_B, l + 1).tobytes() == bc_o.tobytes()
+                e.zero_vec(mgb.VEC_B, l + 1)
+                e.restrict(l, fused=False)        # uses VEC_R written by residual() above
+                assert e.get_vec(mgb.VEC_B, l + 1).tobytes() == bc_o.tobytes()
+                # prolongation + correction, both summation orders
+                uc = rng.uniform(-1, 1, (nci, ncj))
+                e.set_vec(mgb.VEC_U, l + 1, uc)
+                e.set_vec(mgb.VEC_U, l, x)
+                e.prolong(l, multadd=False)
+                want = x.reshape(-1) + 1.0 * o.matmult(2, l, uc.reshape(-1))
+                assert e.get_vec(mgb.VEC_U, l).tobytes() == want.reshape(ni, nj).tobytes()
+                e.set_vec(mgb.VEC_U, l, x)
+                e.prolong(l, multadd=True)
+                want = o.matmultadd(2, l, uc.reshape(-1), x.reshape(-1))
+                assert e.get_vec(mgb.VEC_U, l).tobytes() == want.reshape(ni, nj).tobytes()
+    finally:
+        s.close()
+        o.close()
+
+
+@pytest.mark.parametrize("extra", ["-pc_type sor", "-pc_type sor -pc_sor_omega 1.2", "-pc_type sor -pc_sor_forward",
+                                   "-pc_type sor -pc_sor_backward -pc_sor_omega 0.9", "-pc_type sor -pc_sor_its 2"])
+@pytest.mark.parametrize("npts,levels,mesh", [(17, 2, 0), (129, 3, 0), (65, 3, 2)])
+def test_red_black_sor_bit_exact_vs_oracle(npts, levels, mesh, extra):
+    opts = base(npts, levels, mesh=mesh, mp=3) + " " + extra
+    o = Oracle(opts)
+    s = mgb.Session(opts)
+    e = s.engine
+    sm = mgb.rbsor(omega=1.2 if "1.2" in extra else (0.9 if "0.9" in extra else 1.0),
+                   sweep=mgb.SOR_FORWARD if "forward" in extra else (mgb.SOR_BACKWARD if "backward" in extra else mgb.SOR_SYMMETRIC),
+                   its=2 if "its 2" in extra else 1)
+    rng = np.random.default_rng(7)
+    try:
+        for l in range(levels):
+            ni, nj = e.dims(l)
+            x = rng.uniform(-1, 1, (ni, nj))
+            b = rng.uniform(-1, 1, (ni, nj))
+            e.set_vec(mgb.VEC_B, l, b)
+            for nu, gz in ((1, False), (3, False), (3, True), (1, True)):
+                e.set_vec(mgb.VEC_U, l, x)
+                e.smooth(l, sm, nu, gz)
+                x_g = e.get_vec(mgb.VEC_U, l)
+                x_o = o.to_grid(l, o.smooth(l, o.from_grid(l, b), o.from_grid(l, x), nu, gz))
+                assert x_g.tobytes() == x_o.tobytes(), (l, nu, gz)
+    finally:
+        s.close()
+        o.close()
+
+
+# ------------------------------------------------------------------ end to end against the committed goldens
+E2E = ["n17_l2_jacobi", "n17_l2_jacobi23", "n17_l1_jacobi", "n129_l4_jacobi", "n129_l7_jacobi", "n129_l7_jacobi_v21",
+       "n101_l3_jacobi", "n65_l4_mesh1_jacobi", "n65_l4_mesh2_jacobi", "n129_l7_cg_mg", "n129_l4_cg_mg_jcoarse",
+       "n129_l7_rich_mg_monitor", "n1025_l7_jacobi", "n1025_l10_jacobi",
+       "n17_l2_rbsor", "n129_l4_rbsor", "n129_l7_rbsor", "n129_l7_rbsor_w12", "n1025_l7_rbsor"]
+
+
+@pytest.mark.parametrize("graph", [0, 1])
+@pytest.mark.parametrize("name", E2E)
+def test_end_to_end_matches_golden(name, graph, tmp_path):
+    g = GOLD[name]
+    if graph == 1 and "-cycle 8" in g["options"]:
+        pytest.skip("graph replay only concerns cycle 0")
+    r = mgb.run_poisson(g["options"] + f" -mgb_graph {graph}", out_dir=str(tmp_path))
+    assert r["num_iter"] == g["num_iter"]                                # equal iteration counts
+    want = _hex(g["rnorm_hex"])
+    ok = ~np.isnan(want)
+    assert np.allclose(r["rnorm"][ok], want[ok], rtol=RTOL, atol=0.0)   # per-cycle residual norms, 1e-10 relative
+    err = _hex(g["error_hex"])
+    assert np.allclose(r["error"], err, rtol=RTOL, atol=0.0)
+    u = r["u"]
+    assert list(u.shape) == g["u_shape"]
+    if name in GOLD_U.files:
+        scale = np.abs(GOLD_U[name]).max()
+        assert np.abs(u - GOLD_U[name]).max() <= RTOL * scale             # solution within 1e-10 relative
+    # the files the reference writes (src/solver.c:1331-1354) carry the same numbers
+    rdat = np.array([float(t) for t in open(tmp_path / "rData.dat").read().split()])
+    assert np.array_equal(rdat[ok], r["rnorm"][ok])
+    edat = np.array([float(t) for t in open(tmp_path / "eData.dat").read().split()])
+    assert np.array_equal(edat, r["error"])
+    udat = np.loadtxt(tmp_path / "uData.dat", ndmin=2)
+    assert np.array_equal(udat, u)
+
+
+@pytest.mark.parametrize("name", ["n129_l4_jacobi", "n129_l7_jacobi", "n101_l3_jacobi", "n65_l4_mesh1_jacobi",
+                                  "n129_l7_rbsor", "n1025_l10_jacobi", "n1025_l7_rbsor"])
+def test_cycle0_solution_is_bit_exact(name):
+    """Cycle 0 with Jacobi / red-black smoothing uses no reduction inside the iteration, so the solution vector
+    itself is reproduced bit for bit (only the logged norms differ in summation order)."""
+    g = GOLD[name]
+    r = mgb.run_poisson(g["options"])
+    assert r["num_iter"] == g["num_iter"]
+    assert hashlib.sha256(np.ascontiguousarray(r["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]
+
+
+def test_unsupported_configurations_fail_loudly():
+    for opts in (base(17, 2),                                     # PETSc default PC (ILU) not offered
+                 base(17, 2) + " -pc_type sor",                   # lexicographic SOR not offered
+                 base(17, 2, cycle=1) + " " + JAC,                # research cycle
+                 base(17, 2, cycle=8) + " -ksp_type cg",          # Chebyshev default smoother
+                 "-npts 17 -iter 10 -grids 3 -levels 2 " + JAC):
+        with pytest.raises(mgb.MgbError):
+            mgb.run_poisson(opts)
+
+
+# ------------------------------------------------------------------ full-size properties (no oracle at these sizes)
+@pytest.mark.parametrize("npts,levels", [(4097, 12), (8193, 13)])
+def test_full_size_properties(npts, levels):
+    opts = base(npts, levels, it=40) + " " + JAC + " -mgb_csr 0"
+    s = mgb.Session(opts)
+    e = s.engine
+    try:
+        n = npts - 2
+        # linearity of the stencil on the fine level: A(x + 2y) == A x + 2 A y up to rounding of the sums
+        rng = np.random.default_rng(1)
+        x = rng.uniform(-1, 1, (n, n))
+        y = rng.uniform(-1, 1, (n, n))
+        e.set_vec(mgb.VEC_U, 0, x); e.apply(0, mgb.VEC_U, mgb.VEC_R); ax = e.get_vec(mgb.VEC_R, 0)
+        e.set_vec(mgb.VEC_U, 0, y); e.apply(0, mgb.VEC_U, mgb.VEC_R); ay = e.get_vec(mgb.VEC_R, 0)
+        e.set_vec(mgb.VEC_U, 0, x + 2 * y); e.apply(0, mgb.VEC_U, mgb.VEC_R); axy = e.get_vec(mgb.VEC_R, 0)
+        h2 = float(npts - 1) ** 2
+        assert np.abs(axy - (ax + 2 * ay)).max() <= 64 * np.finfo(float).eps * 8 * h2
+        # exact row of the operator against numpy on a strip (bit for bit, same operation order)
+        c = np.float64(1.0) / (np.float64(1.0 / (n + 1)) * np.float64(1.0 / (n + 1)))
+        i = n // 2
+        want = (c * x[i - 1, 1:-1] + c * x[i, :-2]) + (-2.0 * (c + c)) * x[i, 1:-1]
+        want = (want + c * x[i, 2:]) + c * x[i + 1, 1:-1]
+        assert np.array_equal(ax[i, 1:-1], want)
+        del x, y, ax, ay, axy
+        # solve: textbook convergence (coarsest 1x1 or 3x3), monotone history, discretisation error pi^2 h^2 / 12
+        r = s.solve(want_u=False)
+        assert 6 <= r["num_iter"] <= 12
+        assert np.all(np.diff(r["rnorm"]) < 0)
+        assert r["rnorm"][0] == 1.0 and r["rnorm"][-1] <= 1e-7
+        h = 1.0 / (npts - 1)
+        assert r["error"][0] == pytest.approx(np.pi ** 2 * h * h / 12.0, rel=0.15)
+    finally:
+        s.close()
+
+
+def test_solver_is_deterministic_run_to_run():
+    opts = base(1025, 10) + " " + JAC
+    a = mgb.run_poisson(opts)
+    b = mgb.run_poisson(opts)
+    assert a["num_iter"] == b["num_iter"]
+    assert a["rnorm"].tobytes() == b["rnorm"].tobytes()
+    assert a["u"].tobytes() == b["u"].tobytes()

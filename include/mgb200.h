@@ -170,6 +170,9 @@ int  mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *rnorm, int 
 /* ---- measurement --------------------------------------------------------------------------- */
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 long long mgb_launch_count(const mgb_engine *e);
+/* device time (CUDA events on the engine's stream) of the cycle loop of the last mgb_solve_* call, in ms:
+ * the same region as the reference's MPI_Wtime bracket (ref: src/solver.c:1526-1553) */
+double mgb_last_solve_ms(const mgb_engine *e);
 /* time `reps` back-to-back launches of one operation with CUDA events on the engine's stream;
  * op: 0 apply, 1 residual, 2 jacobi sweep, 3 red-black full sweep (2 half sweeps), 4 fused residual+restrict,
  * 5 prolong+correct, 6 residual norm, 7 csr spmv (A), 8 nrm2, 9 dot, 10 axpy.  ms_per_launch is the average. */

@@ -86,6 +86,8 @@ def engine_lib():
         L.mgb_last_error.restype = C.c_char_p
         L.mgb_launch_count.restype = C.c_longlong
         L.mgb_launch_count.argtypes = [C.c_void_p]
+        L.mgb_last_solve_ms.restype = C.c_double
+        L.mgb_last_solve_ms.argtypes = [C.c_void_p]
         _eng = L
     return _eng
 
@@ -101,6 +103,7 @@ def host_lib():
         L.pb200_run.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(RunResult), C.c_void_p, C.c_void_p, C.c_int]
         L.pb200_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.pb200_solve.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(RunResult), C.c_void_p, C.c_void_p, C.c_int]
+        L.pb200_solve_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RunResult), C.c_void_p, C.c_int]
         L.pb200_close.argtypes = [C.c_void_p]
         L.pb200_session_engine.restype = C.c_void_p
         L.pb200_session_engine.argtypes = [C.c_void_p]
@@ -291,6 +294,9 @@ class Engine:
     def launch_count(self):
         return self.L.mgb_launch_count(self.h)
 
+    def last_solve_ms(self):
+        return self.L.mgb_last_solve_ms(self.h)
+
     def time_op(self, op, l, reps=20):
         ms = C.c_double()
         self._ck(self.L.mgb_time_op(self.h, OPS[op][0], l, reps, C.byref(ms)))
@@ -330,6 +336,17 @@ class Session:
             raise MgbError(f"pb200_solve failed ({rc}): {self.H.pb200_last_error().decode()}")
         return {"num_iter": res.num_iter, "rnorm": rn[: res.num_iter + 1].copy(), "error": np.array(res.error[:]),
                 "u": u, "levels": res.levels, "gpu_launches": res.gpu_launches}
+
+    def solve_rhs(self, b_ptr, u_ptr):
+        """One more Solve() with the right-hand side at host address b_ptr (ni*nj doubles) and the solution copied
+        to host address u_ptr (both plain integers / ctypes pointers, e.g. pinned torch buffers)."""
+        cap = _opt_int(self.options, "-iter") + 2
+        res = RunResult()
+        rn = np.full(cap, np.nan)
+        rc = self.H.pb200_solve_rhs(self.s, C.c_void_p(b_ptr), C.c_void_p(u_ptr), C.byref(res), _pd(rn), cap)
+        if rc != 0:
+            raise MgbError(f"pb200_solve_rhs failed ({rc}): {self.H.pb200_last_error().decode()}")
+        return {"num_iter": res.num_iter, "rnorm": rn[: res.num_iter + 1].copy(), "gpu_launches": res.gpu_launches}
 
     def close(self):
         if getattr(self, "s", None):

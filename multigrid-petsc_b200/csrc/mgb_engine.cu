@@ -61,12 +61,14 @@ struct mgb_engine {
 	Stencil3 R3, P3; bool transfer_set = false;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	double *partial = nullptr;               // MGB_RED_MAXBLOCKS * 3 doubles
+	double *partial = nullptr;               // partial_cap doubles
+	size_t partial_cap = 0;
 	double *scal = nullptr;                  // device scalars
 	double *scal_host = nullptr;             // pinned mirror
 	double *tab_x = nullptr, *tab_y = nullptr; // device tables for separable functions
 	double sor_omega = -1.0;                 // omega for which coef[6] (idiag) is valid
 	long long launches = 0;
+	double last_solve_ms = 0.0;              // CUDA-event time of the last solve loop
 	bool csr_built = false;
 	// graph replay of the cycle (two graphs: the Jacobi ping-pong state alternates between cycles)
 	cudaGraphExec_t gexec[2] = {nullptr, nullptr};
@@ -78,6 +80,8 @@ static LevelDev ldev(const Level &L)
 	return d;
 }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+#define RY_STREAM 32
+static dim3 stream_grid(const Level &L) { return dim3(cdiv(L.pitch, MGB_SB_COLS), cdiv(L.ni, RY_STREAM)); }
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
 #define KCHECK() CU(cudaGetLastError())
 
@@ -125,7 +129,13 @@ extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
 	}
 	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&e->ev0)); CU(cudaEventCreate(&e->ev1));
-	CU(cudaMalloc(&e->partial, sizeof(double) * 3 * MGB_RED_MAXBLOCKS));
+	{
+		// partial sums: one per block of the largest streaming grid (fine level) or 3 per block of k_error
+		const Level &F = e->lev[0];
+		size_t nb = (size_t)cdiv(F.pitch, MGB_SB_COLS) * cdiv(F.ni, RY_STREAM);
+		e->partial_cap = nb > 3 * (size_t)MGB_RED_MAXBLOCKS ? nb : 3 * (size_t)MGB_RED_MAXBLOCKS;
+		CU(cudaMalloc(&e->partial, sizeof(double) * e->partial_cap));
+	}
 	CU(cudaMalloc(&e->scal, sizeof(double) * 64));
 	CU(cudaMallocHost(&e->scal_host, sizeof(double) * 64));
 	for (int l = 0; l < cfg->levels; ++l) {
@@ -170,6 +180,7 @@ extern "C" int mgb_level_dims(const mgb_engine *e, int level, int *ni, int *nj)
 	return MGB_OK;
 }
 extern "C" long long mgb_launch_count(const mgb_engine *e) { return e ? e->launches : 0; }
+extern "C" double mgb_last_solve_ms(const mgb_engine *e) { return e ? e->last_solve_ms : 0.0; }
 
 // ------------------------------------------------------------------------------------------------ operators
 static int upload_coef(mgb_engine *e, Level &L)
@@ -402,8 +413,6 @@ extern "C" int mgb_error_norms_separable(mgb_engine *e, const double *sx, const 
 
 // ------------------------------------------------------------------------------------------------ launch helpers
 // All helpers enqueue on e->stream and do not synchronise.
-#define RY_STREAM 32
-static dim3 stream_grid(const Level &L) { return dim3(cdiv(L.pitch, MGB_SB_COLS), cdiv(L.ni, RY_STREAM)); }
 
 static int k_apply(mgb_engine *e, int l, const double *x, double *y)
 {
@@ -422,7 +431,7 @@ static int k_resnorm(mgb_engine *e, int l, const double *x, const double *b, int
 {
 	Level &L = e->lev[l];
 	const dim3 g = stream_grid(L);
-	if ((long long)g.x * g.y > 3LL * MGB_RED_MAXBLOCKS) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
+	if ((size_t)g.x * g.y > e->partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
 	k_stream5<ST_RESNORM, RY_STREAM><<<g, MGB_SB_THREADS, 0, e->stream>>>(x, b, nullptr, ldev(L), 0.0, e->partial);
 	LAUNCHED(e); KCHECK();
 	k_reduce2<<<1, 1024, 0, e->stream>>>(e->partial, (int)(g.x * g.y), e->scal, slot, 1);
@@ -713,6 +722,7 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 	const int Lc = (int)e->lev.size();
 	if (Lc > 64) return fail(MGB_EINVAL, "too many levels");
 	const auto t0 = std::chrono::steady_clock::now();
+	CU(cudaEventRecord(e->ev0, e->stream));
 	int gphase = 0;
 	while (iter < p->max_iter && 100000000.0 * bnorm > rn && rn > p->rtol * bnorm) {              // :1530
 		if (!p->use_graph || iter == 0) {
@@ -744,9 +754,11 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 		iter = iter + 1;
 		rnorm[iter] = rn;
 	}
+	CU(cudaEventRecord(e->ev1, e->stream));
 	CU(cudaStreamSynchronize(e->stream));
 	const auto t1 = std::chrono::steady_clock::now();
 	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_solve_ms = ms; }
 	drop_graphs(e);
 	const double r0 = rnorm[0];
 	for (int i = 0; i <= iter; ++i) rnorm[i] = rnorm[i] / r0;                                     // :1554-1557
@@ -810,6 +822,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 	TRY(vec_ptr(e, MGB_VEC_Z, 0, &Z)); TRY(vec_ptr(e, MGB_VEC_P, 0, &P)); TRY(vec_ptr(e, MGB_VEC_Q, 0, &Q));
 	CU(cudaStreamSynchronize(e->stream));
 	const auto t0 = std::chrono::steady_clock::now();
+	CU(cudaEventRecord(e->ev0, e->stream));
 	int reason = 0, its = 0, nlog = 0;
 	double rnorm0 = 0.0, ttol = 0.0, dp = 0.0;
 	auto logr = [&](double v) { if (nlog < p->max_iter) rnorm[nlog++] = v; };   // KSPSetResidualHistory(na = numIter)
@@ -869,9 +882,11 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 			if (its >= p->max_iter) { reason = ksp_converged(p, its, dp, &rnorm0, &ttol); if (!reason) reason = -3; }
 		}
 	}
+	CU(cudaEventRecord(e->ev1, e->stream));
 	CU(cudaStreamSynchronize(e->stream));
 	const auto t1 = std::chrono::steady_clock::now();
 	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_solve_ms = ms; }
 	// ref: src/solver.c:1971-1976 -- numIter = KSPGetIterationNumber ; rnorm[i] /= rnorm[0]
 	const double r0 = rnorm[0];
 	for (int i = 0; i < its + 1 && i <= p->max_iter; ++i) rnorm[i] = rnorm[i] / r0;

@@ -174,6 +174,8 @@ int pb200_run(const char *options, const char *dir, pb200_result *res, double *u
 typedef struct pb200_session pb200_session;
 int  pb200_open(const char *options, pb200_session **out);
 int  pb200_solve(pb200_session *s, const char *dir, pb200_result *res, double *u, double *rnorm, int rnorm_cap);
+/* another solve on the assembled session: b (host, ni*nj) replaces the right-hand side, u (host) receives the solution */
+int  pb200_solve_rhs(pb200_session *s, const double *b, double *u, pb200_result *res, double *rnorm, int rnorm_cap);
 void pb200_close(pb200_session *s);
 struct mgb_engine *pb200_session_engine(pb200_session *s);
 const char *pb200_last_error(void);

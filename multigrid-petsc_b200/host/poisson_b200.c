@@ -48,6 +48,7 @@ typedef struct pb200_session {
 	Problem prob; Mesh mesh; Indices indices; Operator op; Solver solver; PostProcess pp;
 	int cyc, meshflag, mapflag;
 	int assembled, solved;
+	int max_iter;                       /* -iter as given (Solve overwrites solver.numIter with the count done) */
 } pb200_session;
 
 /* SetUpProblem .. Assemble (ref: src/poisson.c:45-118) from the options database */
@@ -101,6 +102,7 @@ static int session_setup(pb200_session *s)
 	SetUpSolver(&s->indices, &s->solver, s->cyc == 0 ? VCYCLE : PetscPCMG);
 	Assemble(&s->prob, &s->mesh, &s->indices, &s->op, &s->solver);
 	s->assembled = 1;
+	s->max_iter = s->solver.numIter;
 	return 0;
 }
 
@@ -191,6 +193,30 @@ int pb200_solve(pb200_session *s, const char *dir, pb200_result *res, double *u,
 	pb200_trap = NULL;
 	quiet_end(saved);
 	if (rc == 0) session_results(s, res, u, rnorm, rnorm_cap);
+	return rc;
+}
+
+/* One more solve on an assembled session with a caller-supplied right-hand side (host, ni*nj doubles, natural
+ * order -- what levelvecb would have put into b[0], ref: src/solver.c:594-597) and the solution copied back to a
+ * host buffer (what GetSol does, ref: src/solver.c:1255-1313).  No files, no error norms. */
+int pb200_solve_rhs(pb200_session *s, const double *b, double *u, pb200_result *res, double *rnorm, int rnorm_cap)
+{
+	jmp_buf trap;
+	if (!s || !b) return 2;
+	const int saved = quiet_begin();
+	int rc = 0;
+	pb200_trap = &trap;
+	if (setjmp(trap) == 0) {
+		s->solver.numIter = s->max_iter;
+		if (mgb_set_rhs(pb200_engine(&s->solver), b) != MGB_OK) rc = 1;
+		else Solve(&s->solver);
+	} else rc = 1;
+	pb200_trap = NULL;
+	quiet_end(saved);
+	if (rc == 0) {
+		memset(s->pp.error, 0, sizeof s->pp.error);
+		session_results(s, res, u, rnorm, rnorm_cap);
+	}
 	return rc;
 }
 

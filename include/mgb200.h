@@ -88,7 +88,8 @@ typedef struct {
 	int red_black_numbering; /* 1: -map 3 extension (CSR assembly is then not offered)      */
 	/* strip decomposition (one engine per rank; rank 0 of 1 on a single GPU) */
 	int rank, nranks;
-	int agglomerate_below; /* levels with ni <= this are kept whole on rank 0 (multi-GPU only) */
+	int agglomerate_below; /* levels with ni <= this are kept whole on rank 0 (multi-GPU only; 0 = default 511) */
+	int emulate;           /* 1: hold ALL nranks strips in this process on one GPU, run them in lock step (tests) */
 } mgb_config;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -96,6 +97,20 @@ int  mgb_create(const mgb_config *cfg, mgb_engine **out);
 int  mgb_destroy(mgb_engine *e);
 const char *mgb_last_error(void);
 int  mgb_version(void);
+/* ---- row strips over several GPUs (replaces the reference's per-rank row ranges, ref: src/matbuild.c:120-144,
+ * and the MPI plumbing PETSc does for it) ------------------------------------------------------------------
+ * One process per GPU creates an engine with (rank, nranks); mgb_ipc_export gives a 64-byte CUDA IPC handle of
+ * the engine's HBM arena; the handles of all ranks, concatenated in rank order (exchanged by the caller, e.g.
+ * with torch.distributed.all_gather), go to mgb_ipc_connect.  After that every call below is COLLECTIVE: all
+ * ranks must make the same calls in the same order.  Host vectors stay whole-grid arrays; each rank reads /
+ * writes only its own rows of them (mgb_local_rows). */
+#define MGB_IPC_HANDLE_BYTES 64
+int  mgb_ipc_export(mgb_engine *e, void *handle);
+int  mgb_ipc_connect(mgb_engine *e, const void *handles);
+int  mgb_local_rows(const mgb_engine *e, int level, int *row0, int *row1);
+/* the partition itself (host arithmetic, no GPU needed): rows [row0,row1) of `level` that `rank` handles */
+int  mgb_strip_rows(const mgb_config *cfg, int level, int rank, int *row0, int *row1, int *distributed);
+
 /* dimensions of level l as the engine derived them (ref: src/matbuild.c:64-66: n_l = (N-1)/2^l - 1) */
 int  mgb_level_dims(const mgb_engine *e, int level, int *ni, int *nj);
 

@@ -27,6 +27,7 @@ MAT_A, MAT_RES, MAT_PRO = range(3)
 SMOOTH_JACOBI, SMOOTH_RBSOR = 0, 1
 SOR_SYMMETRIC, SOR_FORWARD, SOR_BACKWARD = 0, 1, 2
 KSP_RICHARDSON, KSP_CG = 0, 1
+IPC_HANDLE_BYTES = 64
 COARSE_LU, COARSE_RICHARDSON = 0, 1
 # mgb_time_op codes and their algorithmic HBM bytes per (fine) unknown (SURVEY.md 8d / DESIGN.md)
 OPS = {"apply": (0, 16), "residual": (1, 24), "jacobi": (2, 24), "rbsor_full": (3, 48), "residual_restrict": (4, 18),
@@ -38,6 +39,17 @@ class MgbError(RuntimeError):
     pass
 
 
+def strip_rows(levels, ni, nj, nranks, level, rank, agglomerate_below=0):
+    """The row partition of the engine (host arithmetic, works without a GPU): (row0, row1, distributed)."""
+    L = engine_lib()
+    cfg = Config(levels, ni, nj, -1, 0, 0, nranks, agglomerate_below, 0)
+    a, b, d = C.c_int(), C.c_int(), C.c_int()
+    rc = L.mgb_strip_rows(C.byref(cfg), level, rank, C.byref(a), C.byref(b), C.byref(d))
+    if rc != 0:
+        raise MgbError(f"mgb error {rc}: {L.mgb_last_error().decode()}")
+    return a.value, b.value, bool(d.value)
+
+
 class Smoother(C.Structure):
     _fields_ = [("type", C.c_int), ("scale", C.c_double), ("omega", C.c_double), ("sor_sweep", C.c_int),
                 ("sor_its", C.c_int)]
@@ -46,7 +58,7 @@ class Smoother(C.Structure):
 class Config(C.Structure):
     _fields_ = [("levels", C.c_int), ("ni", C.c_int), ("nj", C.c_int), ("device", C.c_int),
                 ("red_black_numbering", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
-                ("agglomerate_below", C.c_int)]
+                ("agglomerate_below", C.c_int), ("emulate", C.c_int)]
 
 
 class VcycleParams(C.Structure):
@@ -126,7 +138,8 @@ def rbsor(omega=1.0, sweep=SOR_SYMMETRIC, its=1):
 class Engine:
     """One engine instance (one GPU).  Thin wrapper: every method is one C-ABI call of include/mgb200.h."""
 
-    def __init__(self, levels, ni, nj=None, device=-1, red_black_numbering=False, _borrow=None):
+    def __init__(self, levels, ni, nj=None, device=-1, red_black_numbering=False, rank=0, nranks=1,
+                 agglomerate_below=0, emulate=False, _borrow=None):
         self.L = engine_lib()
         self.levels = levels
         self._owned = _borrow is None
@@ -134,7 +147,7 @@ class Engine:
             self.h = C.c_void_p(_borrow)
             return
         nj = ni if nj is None else nj
-        cfg = Config(levels, ni, nj, device, int(red_black_numbering), 0, 1, 0)
+        cfg = Config(levels, ni, nj, device, int(red_black_numbering), rank, nranks, agglomerate_below, int(emulate))
         self.h = C.c_void_p()
         self._ck(self.L.mgb_create(C.byref(cfg), C.byref(self.h)))
 
@@ -153,6 +166,21 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # row strips: IPC handle exchange is the caller's job (multigrid-petsc_b200/strips.py does it with torch.distributed)
+    def ipc_export(self):
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._ck(self.L.mgb_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_connect(self, handles):
+        """handles: the concatenation of every rank's ipc_export(), in rank order"""
+        self._ck(self.L.mgb_ipc_connect(self.h, C.c_char_p(bytes(handles))))
+
+    def local_rows(self, l):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.mgb_local_rows(self.h, l, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def dims(self, l):
         ni, nj = C.c_int(), C.c_int()

@@ -99,10 +99,11 @@ k_error(const double *__restrict__ u, const double *__restrict__ sx, const doubl
 		partial[3 * blockIdx.x + 0] = m; partial[3 * blockIdx.x + 1] = t1; partial[3 * blockIdx.x + 2] = t2;
 	}
 }
-__global__ void k_error2(const double *__restrict__ partial, int n, double *__restrict__ out)
+// finalize = 0 leaves the sum of squares unrooted (several strips are combined by the caller)
+__global__ void k_error2(const double *__restrict__ partial, int n, double *__restrict__ out, int finalize)
 {
 	if (threadIdx.x != 0) return;
 	double m = 0.0, s1 = 0.0, s2 = 0.0;
 	for (int k = 0; k < n; ++k) { m = fmax(m, partial[3 * k]); s1 += partial[3 * k + 1]; s2 += partial[3 * k + 2]; }
-	out[0] = m; out[1] = s1; out[2] = sqrt(s2);
+	out[0] = m; out[1] = s1; out[2] = finalize ? sqrt(s2) : s2;
 }

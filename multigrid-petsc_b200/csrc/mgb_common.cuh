@@ -6,7 +6,8 @@
 //     and >= nj + 1;
 //   * columns nj .. pitch-1 of every row are ZERO: they are the right Dirichlet ghost of row i and, at
 //     address (i+1)*pitch - 1, the left ghost (j = -1) of row i+1;
-//   * G ghost rows above row 0 and below row ni-1: zero on a single GPU (Dirichlet), neighbour rows on a strip;
+//   * MGB_GHOST_ROWS ghost rows above row 0 and below row ni-1: zero at the physical boundary (Dirichlet),
+//     copies of the neighbour strips' boundary rows otherwise (pushed by mgb_halo.cuh after every write);
 //   * element (0,0) is 128-byte aligned.
 // With that layout the 5-point stencil needs no boundary branches and every row start is aligned for
 // 16-byte vector loads (for the reference's n = 2^k - 1 grids pitch == n + 1 exactly: no wasted bytes).
@@ -18,7 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define MGB_GHOST_ROWS 1
+#define MGB_GHOST_ROWS 6     // ghost rows above and below every strip (room for fused multi-sweep kernels)
 #define MGB_COEF_STRIDE 8     // doubles per grid row in the coefficient table: S W C E N dinv idiag mdiag
 
 struct LevelDev {
@@ -26,6 +27,7 @@ struct LevelDev {
 	int pitch;           // doubles per row
 	int i0;              // global grid-row index of local row 0 (0 on a single GPU)
 	int uniform;         // 1: every grid row has the same coefficients (mesh 0)
+	int rb;              // 1: red-black numbering (-map 3): row sums run in ascending RED-FIRST column order
 	const double *coef;  // MGB_COEF_STRIDE doubles per GLOBAL grid row
 };
 
@@ -46,6 +48,22 @@ __device__ __forceinline__ double stencil5(double aS, double aW, double aC, doub
 	s = add(s, mul(aC, xC));
 	s = add(s, mul(aE, xE));
 	s = add(s, mul(aN, xN));
+	return s;
+}
+
+// The same row sum when the unknowns are numbered red-first (-map 3; red = (i+j) even): a red row stores its
+// diagonal first (every black neighbour has a higher number), a black row stores it last; within one colour the
+// natural order S < W < E < N is kept.  order: 0 natural, 1 red row, 2 black row.
+__device__ __forceinline__ double stencil5_ord(int order, double aS, double aW, double aC, double aE, double aN,
+                                               double xS, double xW, double xC, double xE, double xN)
+{
+	if (order == 0) return stencil5(aS, aW, aC, aE, aN, xS, xW, xC, xE, xN);
+	double s;
+	if (order == 1) { s = mul(aC, xC); s = add(s, mul(aS, xS)); } else s = mul(aS, xS);
+	s = add(s, mul(aW, xW));
+	s = add(s, mul(aE, xE));
+	s = add(s, mul(aN, xN));
+	if (order == 2) s = add(s, mul(aC, xC));
 	return s;
 }
 

@@ -1,14 +1,24 @@
 // mgb_engine.cu -- the B200 multigrid engine behind include/mgb200.h.
 //
-// Host-side orchestration (level hierarchy, HBM allocation, kernel sequencing of the V-cycle and of the
-// MG-preconditioned Krylov wrapper, CUDA-graph replay) plus the extern "C" entry points.  The kernels are in
-// mgb_stencil.cuh / mgb_transfer.cuh / mgb_blas.cuh / mgb_csr.cuh / mgb_coarse.cuh.  There is NO CPU fallback:
-// every entry point fails with MGB_ECUDA when no device is usable.
+// Host-side orchestration (level hierarchy, row-strip decomposition, HBM arena, kernel sequencing of the V-cycle
+// and of the MG-preconditioned Krylov wrapper, CUDA-graph replay) plus the extern "C" entry points.  The kernels
+// are in mgb_stencil.cuh / mgb_transfer.cuh / mgb_blas.cuh / mgb_csr.cuh / mgb_coarse.cuh / mgb_halo.cuh.
+// There is NO CPU fallback: every entry point fails with MGB_ECUDA when no device is usable.
 //
 // Reference sequencing that this file reproduces ("ref:" = /root/reference):
 //   cycle 0  MultigridVcycle      ref: src/solver.c:1414-1575 (hot loop :1530-1550)
 //   cycle 8  MultigridPetscPCMG   ref: src/solver.c:1884-1989, with PETSc's KSPCG / KSPRICHARDSON / PCMG
 //            semantics as restated in oracle/minipetsc/minipetsc.c ([PETSc-upstream], unpinned).
+//   row ranges per rank           ref: src/matbuild.c:120-144 (GetRanges) -- re-designed as whole-row strips
+//
+// Strips.  With nranks > 1 the levels whose row count exceeds cfg.agglomerate_below are split into contiguous
+// row strips, one per rank (= one GPU, one process); the coarser levels live whole on rank 0.  The partition is
+// defined on the first agglomerated level (rows c_r = floor(r * n / P)) and doubled upwards (rank r owns fine
+// rows [2 c_r, 2 c_{r+1}), the last rank also the final row), so that restriction needs one foreign residual
+// row and prolongation one foreign coarse row.  Every kernel that writes a distributed vector is
+// followed by a ghost-row push into the neighbours' HBM (mgb_halo.cuh).  A process holds ONE strip in
+// production (peers reached through CUDA IPC) or ALL strips on one GPU when cfg.emulate is set (tests: the
+// same kernels and the same protocol, launched in lock step on one stream).
 #include "../../include/mgb200.h"
 #include "mgb_common.cuh"
 #include "mgb_stencil.cuh"
@@ -16,6 +26,7 @@
 #include "mgb_blas.cuh"
 #include "mgb_csr.cuh"
 #include "mgb_coarse.cuh"
+#include "mgb_halo.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -35,193 +46,415 @@ static int fail(int code, const char *fmt, ...)
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) \
 	return fail(MGB_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); } while (0)
 #define TRY(call) do { int _r = (call); if (_r != MGB_OK) return _r; } while (0)
+#define KCHECK() CU(cudaGetLastError())
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------ engine state
+#define MGB_MAXL 32
+#define NOOFF ((size_t)-1)
+// channels: halo of (level, physical buffer), then gather / broadcast per level, then the all-reduce
+#define CH_HALO(l, k) ((l) * MGB_NVEC + (k))
+#define CH_GATHER(l)  (MGB_MAXL * MGB_NVEC + (l))
+#define CH_BCAST(l)   (MGB_MAXL * MGB_NVEC + MGB_MAXL + (l))
+#define CH_REDUCE     (MGB_MAXL * MGB_NVEC + 2 * MGB_MAXL)
+#define MGB_NCHAN     (CH_REDUCE + 1)
+#define RED_VALS 4                          // doubles per rank slot of the all-reduce
+#define SC_LOCAL 32                         // scal[] index where a strip parks its local partial before the all-reduce
+
 struct Csr {
 	int m = 0, n = 0; long long nnz = 0;
 	int *rowptr = nullptr, *col = nullptr; double *val = nullptr;
 };
 
-struct Level {
-	int ni = 0, nj = 0, pitch = 0;
-	size_t alloc = 0, origin = 0;            // doubles per vector allocation, offset of element (0,0)
-	double *base[MGB_NVEC] = {};
-	double *v[MGB_NVEC] = {};                // v[k] = base[k] + origin (the two ping-pong buffers may swap)
-	std::vector<double> coef_host;           // ni * MGB_COEF_STRIDE
-	double *coef = nullptr;
+// geometry of one level: global part, identical on every rank
+struct LevelGeom {
+	int gni = 0, nj = 0, pitch = 0;
+	bool dist = false;                       // split into row strips (else whole, on rank 0)
+	int rows[MGB_MAX_RANKS + 1] = {};        // partition: rank r handles global rows [rows[r], rows[r+1])
+	std::vector<double> coef_host;           // gni * MGB_COEF_STRIDE
 	bool coef_set = false;
 	int uniform = 1;
-	Csr A, R, P;                             // R, P: this level (fine) <-> level+1
-	BandLU lu;                               // coarse LU (cycle 8, coarsest level only)
+};
+
+// arena layout of one rank (a pure function of the configuration, so every rank can address its peers)
+struct Layout {
+	size_t vec_off[MGB_MAXL][MGB_NVEC];      // byte offset of each vector allocation, NOOFF if absent
+	size_t origin[MGB_MAXL];                 // doubles from allocation start to element (0,0)
+	size_t alloc[MGB_MAXL];                  // doubles per vector allocation
+	int ni[MGB_MAXL], r0[MGB_MAXL];          // local rows / first global row on this rank
+	size_t flags_off, slots_off, ver_off, ticket_off, status_off, total;
+};
+
+struct SLevel {                              // one level on one strip
+	int ni = 0, r0 = 0;
+	bool present = false;                    // arrays exist on this strip
+	bool active = false;                     // this strip computes on the level (dist, or whole on rank 0)
+	double *base[MGB_NVEC] = {};
+	double *v[MGB_NVEC] = {};                // v[k] = pointer to element (0,0); the Jacobi ping-pong swaps two of them
+	int phys[MGB_NVEC] = {};                 // which physical allocation v[k] currently points into
+	double *coef = nullptr;                  // device copy of LevelGeom::coef_host (all global rows)
+	Csr A, R, P;
+	BandLU lu;
+};
+
+struct Strip {
+	int rank = 0, device = 0;
+	char *arena = nullptr;
+	std::vector<SLevel> lev;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double *partial = nullptr; size_t partial_cap = 0;
+	double *scal = nullptr, *scal_host = nullptr;
+	double *tab_x = nullptr, *tab_y = nullptr;
+	int *status_host = nullptr;
 };
 
 struct mgb_engine {
 	mgb_config cfg;
-	std::vector<Level> lev;
+	int P = 1, L = 1, La = 0;                // ranks, levels, first agglomerated level (== L: none)
+	std::vector<LevelGeom> geo;
+	std::vector<Layout> lay;                 // per rank
+	std::vector<Strip> strips;               // local strips: 1 (production) or P (emulation)
+	char *arena_of[MGB_MAX_RANKS] = {};      // arena base of every rank as addressable from this process
+	bool peer_opened[MGB_MAX_RANKS] = {};
+	bool connected = false;
 	Stencil3 R3, P3; bool transfer_set = false;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	double *partial = nullptr;               // partial_cap doubles
-	size_t partial_cap = 0;
-	double *scal = nullptr;                  // device scalars
-	double *scal_host = nullptr;             // pinned mirror
-	double *tab_x = nullptr, *tab_y = nullptr; // device tables for separable functions
-	double sor_omega = -1.0;                 // omega for which coef[6] (idiag) is valid
+	double sor_omega = -1.0;
 	long long launches = 0;
-	double last_solve_ms = 0.0;              // CUDA-event time of the last solve loop
+	double last_solve_ms = 0.0;
 	bool csr_built = false;
-	// graph replay of the cycle (two graphs: the Jacobi ping-pong state alternates between cycles)
 	cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
 };
+#define LAUNCHED(e) do { (e)->launches++; } while (0)
 
-static LevelDev ldev(const Level &L)
+// ------------------------------------------------------------------------------------------------ partition + layout
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int build_geometry(const mgb_config *cfg, std::vector<LevelGeom> &geo, int *La_out)
 {
-	LevelDev d; d.ni = L.ni; d.nj = L.nj; d.pitch = L.pitch; d.i0 = 0; d.uniform = L.uniform; d.coef = L.coef;
+	const int L = cfg->levels, P = cfg->nranks < 1 ? 1 : cfg->nranks;
+	geo.assign(L, LevelGeom());
+	for (int l = 0; l < L; ++l) {
+		// level sizes: n_l = (N-1)/2^l - 1 with N-1 = n_0 + 1   (ref: src/matbuild.c:64-66)
+		geo[l].gni = (cfg->ni + 1) / (1 << l) - 1;
+		geo[l].nj = (cfg->nj + 1) / (1 << l) - 1;
+		if (geo[l].gni < 1 || geo[l].nj < 1) return fail(MGB_EINVAL, "level %d has no interior points", l);
+		geo[l].pitch = ((geo[l].nj + 1 + 15) / 16) * 16;
+		geo[l].coef_host.assign((size_t)geo[l].gni * MGB_COEF_STRIDE, 0.0);
+	}
+	int La = L;
+	if (P > 1) {
+		const int thr = cfg->agglomerate_below > 0 ? cfg->agglomerate_below : 511;
+		for (int l = 0; l < L; ++l) if (geo[l].gni <= thr) { La = l; break; }
+		if (La == 0) return fail(MGB_EINVAL, "the finest level (%d rows) is not above agglomerate_below = %d: nothing to distribute over %d ranks",
+		                         geo[0].gni, thr, P);
+		// base partition on the first agglomerated level (or on the coarsest level when nothing is agglomerated)
+		const int lb = La < L ? La : L - 1;
+		for (int r = 0; r <= P; ++r) geo[lb].rows[r] = (int)((long long)r * geo[lb].gni / P);
+		for (int l = lb - 1; l >= 0; --l) {
+			// the coarse grid row I sits on fine row 2I+1 (ref: src/solver.c:231-232): fine rows [2 c_r, 2 c_{r+1})
+			for (int r = 0; r < P; ++r) geo[l].rows[r] = 2 * geo[l + 1].rows[r];
+			geo[l].rows[P] = geo[l].gni;
+		}
+		for (int l = 0; l < La; ++l) {
+			geo[l].dist = true;
+			for (int r = 0; r < P; ++r)
+				if (geo[l].rows[r + 1] - geo[l].rows[r] < 2 * MGB_GHOST_ROWS)
+					return fail(MGB_EINVAL, "level %d: rank %d would hold %d rows (< %d): too many ranks for this grid, raise "
+					            "agglomerate_below", l, r, geo[l].rows[r + 1] - geo[l].rows[r], 2 * MGB_GHOST_ROWS);
+		}
+	}
+	for (int l = 0; l < L; ++l)
+		if (!geo[l].dist && !(P > 1 && l == La)) { geo[l].rows[0] = 0; for (int r = 1; r <= P; ++r) geo[l].rows[r] = geo[l].gni; }
+	*La_out = La;
+	return MGB_OK;
+}
+
+static void build_layout(const mgb_config *cfg, const std::vector<LevelGeom> &geo, int La, int rank, Layout &y)
+{
+	const int L = cfg->levels;
+	size_t off = 0;
+	for (int l = 0; l < MGB_MAXL; ++l) for (int k = 0; k < MGB_NVEC; ++k) y.vec_off[l][k] = NOOFF;
+	for (int l = 0; l < L; ++l) {
+		const LevelGeom &g = geo[l];
+		const bool present = g.dist || rank == 0 || l == La;       // rank != 0 keeps staging arrays of level La only
+		y.ni[l] = g.dist ? g.rows[rank + 1] - g.rows[rank] : g.gni;
+		y.r0[l] = g.dist ? g.rows[rank] : 0;
+		y.origin[l] = (size_t)MGB_GHOST_ROWS * g.pitch + 16;
+		y.alloc[l] = (size_t)(y.ni[l] + 2 * MGB_GHOST_ROWS + 1) * g.pitch + 32;
+		if (!present) continue;
+		const int nvec = (l == 0) ? MGB_NVEC : MGB_VEC_W + 1;      // Krylov work vectors exist on the finest level only
+		for (int k = 0; k < nvec; ++k) { y.vec_off[l][k] = off; off = align_up(off + y.alloc[l] * sizeof(double), 256); }
+	}
+	y.flags_off = off;  off = align_up(off + sizeof(unsigned long long) * MGB_NCHAN * MGB_MAX_RANKS, 256);
+	y.slots_off = off;  off = align_up(off + sizeof(double) * 2 * MGB_MAX_RANKS * RED_VALS, 256);
+	y.ver_off = off;    off = align_up(off + sizeof(unsigned long long) * MGB_NCHAN, 256);
+	y.ticket_off = off; off = align_up(off + sizeof(unsigned int) * MGB_NCHAN, 256);
+	y.status_off = off; off = align_up(off + 256, 256);
+	y.total = off;
+}
+
+// the row partition (host arithmetic only, usable without a GPU)
+extern "C" int mgb_strip_rows(const mgb_config *cfg, int level, int rank, int *row0, int *row1, int *distributed)
+{
+	if (!cfg || level < 0 || level >= cfg->levels || rank < 0 || rank >= (cfg->nranks < 1 ? 1 : cfg->nranks))
+		return fail(MGB_EINVAL, "bad argument");
+	if (cfg->levels > MGB_MAXL) return fail(MGB_EINVAL, "too many levels");
+	std::vector<LevelGeom> geo; int La;
+	TRY(build_geometry(cfg, geo, &La));
+	const bool part = geo[level].dist || ((cfg->nranks > 1) && level == La);
+	if (row0) *row0 = part ? geo[level].rows[rank] : 0;
+	if (row1) *row1 = part ? geo[level].rows[rank + 1] : geo[level].gni;
+	if (distributed) *distributed = geo[level].dist ? 1 : 0;
+	return MGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small accessors
+static LevelDev ldev(const mgb_engine *e, const Strip &s, int l)
+{
+	LevelDev d; d.ni = s.lev[l].ni; d.nj = e->geo[l].nj; d.pitch = e->geo[l].pitch; d.i0 = s.lev[l].r0;
+	d.uniform = e->geo[l].uniform; d.rb = e->cfg.red_black_numbering ? 1 : 0; d.coef = s.lev[l].coef;
 	return d;
 }
-static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-#define RY_STREAM 32
-static dim3 stream_grid(const Level &L) { return dim3(cdiv(L.pitch, MGB_SB_COLS), cdiv(L.ni, RY_STREAM)); }
-#define LAUNCHED(e) do { (e)->launches++; } while (0)
-#define KCHECK() CU(cudaGetLastError())
-
-static int vec_ptr(mgb_engine *e, int which, int level, double **out)
+// view of rows [c0, c1) of a whole (agglomerated) level held in full on this strip
+static LevelDev ldev_rows(const mgb_engine *e, const Strip &s, int l, int c0, int c1)
 {
-	if (level < 0 || level >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d out of range", level);
+	LevelDev d = ldev(e, s, l); d.ni = c1 - c0; d.i0 = c0; return d;
+}
+static int check_vec(const mgb_engine *e, int which, int level)
+{
+	if (level < 0 || level >= e->L) return fail(MGB_EINVAL, "level %d out of range", level);
 	if (which < 0 || which >= MGB_NVEC) return fail(MGB_EINVAL, "vector id %d out of range", which);
-	Level &L = e->lev[level];
-	if (!L.base[which]) {
-		CU(cudaMalloc(&L.base[which], L.alloc * sizeof(double)));
-		CU(cudaMemsetAsync(L.base[which], 0, L.alloc * sizeof(double), e->stream));
-		L.v[which] = L.base[which] + L.origin;
-	}
-	*out = L.v[which];
+	if (level > 0 && which > MGB_VEC_W) return fail(MGB_EINVAL, "Krylov work vectors (ids > %d) exist on the finest level only", MGB_VEC_W);
+	return MGB_OK;
+}
+static unsigned long long *flags_of(mgb_engine *e, int rank) { return (unsigned long long *)(e->arena_of[rank] + e->lay[rank].flags_off); }
+static double *slots_of(mgb_engine *e, int rank) { return (double *)(e->arena_of[rank] + e->lay[rank].slots_off); }
+static unsigned long long *ver_of(mgb_engine *e, const Strip &s) { return (unsigned long long *)(s.arena + e->lay[s.rank].ver_off); }
+static unsigned int *ticket_of(mgb_engine *e, const Strip &s) { return (unsigned int *)(s.arena + e->lay[s.rank].ticket_off); }
+static int *status_of(mgb_engine *e, const Strip &s) { return (int *)(s.arena + e->lay[s.rank].status_off); }
+// element (0,0) of physical buffer k of level l on rank r, as addressable from this process
+static double *peer_vec(mgb_engine *e, int r, int l, int k)
+{
+	return (double *)(e->arena_of[r] + e->lay[r].vec_off[l][k]) + e->lay[r].origin[l];
+}
+static int need_peers(mgb_engine *e)
+{
+	if (e->P > 1 && !e->connected) return fail(MGB_ESTATE, "multi-rank engine: call mgb_ipc_export / mgb_ipc_connect on every rank first");
 	return MGB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ lifetime
-extern "C" int mgb_version(void) { return 100; }
+extern "C" int mgb_version(void) { return 200; }
 extern "C" const char *mgb_last_error(void) { return g_err; }
-
-extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
-{
-	if (!cfg || !out) return fail(MGB_EINVAL, "null argument");
-	if (cfg->levels < 1 || cfg->ni < 1 || cfg->nj < 1) return fail(MGB_EINVAL, "levels, ni, nj must be positive");
-	if (cfg->nranks > 1) return fail(MGB_EINVAL, "strip decomposition goes through mgb_create_strip (not in this build)");
-	int ndev = 0;
-	cudaError_t ce = cudaGetDeviceCount(&ndev);
-	if (ce != cudaSuccess || ndev < 1)
-		return fail(MGB_ECUDA, "no CUDA device available (%s): the B200 engine has no CPU fallback", cudaGetErrorString(ce));
-	if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
-	mgb_engine *e = new mgb_engine();
-	e->cfg = *cfg;
-	e->lev.resize(cfg->levels);
-	// level sizes: n_l = (N-1)/2^l - 1 with N-1 = n_0 + 1   (ref: src/matbuild.c:64-66)
-	for (int l = 0; l < cfg->levels; ++l) {
-		Level &L = e->lev[l];
-		L.ni = (cfg->ni + 1) / (1 << l) - 1;
-		L.nj = (cfg->nj + 1) / (1 << l) - 1;
-		if (L.ni < 1 || L.nj < 1) { delete e; return fail(MGB_EINVAL, "level %d has no interior points", l); }
-		L.pitch = ((L.nj + 1 + 15) / 16) * 16;
-		L.origin = (size_t)MGB_GHOST_ROWS * L.pitch + 16;
-		L.alloc = (size_t)(L.ni + 2 * MGB_GHOST_ROWS + 1) * L.pitch + 32;
-		L.coef_host.assign((size_t)L.ni * MGB_COEF_STRIDE, 0.0);
-	}
-	CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-	CU(cudaEventCreate(&e->ev0)); CU(cudaEventCreate(&e->ev1));
-	{
-		// partial sums: one per block of the largest streaming grid (fine level) or 3 per block of k_error
-		const Level &F = e->lev[0];
-		size_t nb = (size_t)cdiv(F.pitch, MGB_SB_COLS) * cdiv(F.ni, RY_STREAM);
-		e->partial_cap = nb > 3 * (size_t)MGB_RED_MAXBLOCKS ? nb : 3 * (size_t)MGB_RED_MAXBLOCKS;
-		CU(cudaMalloc(&e->partial, sizeof(double) * e->partial_cap));
-	}
-	CU(cudaMalloc(&e->scal, sizeof(double) * 64));
-	CU(cudaMallocHost(&e->scal_host, sizeof(double) * 64));
-	for (int l = 0; l < cfg->levels; ++l) {
-		Level &L = e->lev[l];
-		CU(cudaMalloc(&L.coef, sizeof(double) * L.coef_host.size()));
-		double *p;
-		for (int k = 0; k <= MGB_VEC_W; ++k) { int r = vec_ptr(e, k, l, &p); if (r) { return r; } }
-	}
-	CU(cudaMalloc(&e->tab_x, sizeof(double) * (size_t)(cfg->nj + 16)));
-	CU(cudaMalloc(&e->tab_y, sizeof(double) * (size_t)(cfg->ni + 16)));
-	CU(cudaStreamSynchronize(e->stream));
-	*out = e;
-	return MGB_OK;
-}
 
 static void free_csr(Csr &c) { cudaFree(c.rowptr); cudaFree(c.col); cudaFree(c.val); c = Csr(); }
 
 extern "C" int mgb_destroy(mgb_engine *e)
 {
 	if (!e) return MGB_OK;
-	cudaStreamSynchronize(e->stream);
+	for (auto &s : e->strips) if (s.stream) cudaStreamSynchronize(s.stream);
 	for (int g = 0; g < 2; ++g) if (e->gexec[g]) cudaGraphExecDestroy(e->gexec[g]);
-	for (auto &L : e->lev) {
-		for (int k = 0; k < MGB_NVEC; ++k) cudaFree(L.base[k]);
-		cudaFree(L.coef);
-		free_csr(L.A); free_csr(L.R); free_csr(L.P);
-		bandlu_free(L.lu);
+	for (int r = 0; r < MGB_MAX_RANKS; ++r) if (e->peer_opened[r]) cudaIpcCloseMemHandle(e->arena_of[r]);
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i];
+		for (auto &L : s.lev) { cudaFree(L.coef); free_csr(L.A); free_csr(L.R); free_csr(L.P); bandlu_free(L.lu); }
+		cudaFree(s.arena); cudaFree(s.partial); cudaFree(s.scal); cudaFreeHost(s.scal_host); cudaFreeHost(s.status_host);
+		cudaFree(s.tab_x); cudaFree(s.tab_y);
+		if (s.ev0) cudaEventDestroy(s.ev0);
+		if (s.ev1) cudaEventDestroy(s.ev1);
+		if (s.stream && i == 0) cudaStreamDestroy(s.stream);       // emulated strips share the stream of strip 0
 	}
-	cudaFree(e->partial); cudaFree(e->scal); cudaFreeHost(e->scal_host);
-	cudaFree(e->tab_x); cudaFree(e->tab_y);
-	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
-	cudaStreamDestroy(e->stream);
 	delete e;
+	return MGB_OK;
+}
+
+extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
+{
+	if (!cfg || !out) return fail(MGB_EINVAL, "null argument");
+	if (cfg->levels < 1 || cfg->ni < 1 || cfg->nj < 1) return fail(MGB_EINVAL, "levels, ni, nj must be positive");
+	if (cfg->levels > MGB_MAXL) return fail(MGB_EINVAL, "at most %d levels", MGB_MAXL);
+	const int P = cfg->nranks < 1 ? 1 : cfg->nranks;
+	if (P > MGB_MAX_RANKS) return fail(MGB_EINVAL, "at most %d ranks (one NVSwitch domain)", MGB_MAX_RANKS);
+	if (cfg->rank < 0 || cfg->rank >= P) return fail(MGB_EINVAL, "rank %d out of range", cfg->rank);
+	int ndev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev < 1)
+		return fail(MGB_ECUDA, "no CUDA device available (%s): the B200 engine has no CPU fallback", cudaGetErrorString(ce));
+	if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
+	int dev = 0; CU(cudaGetDevice(&dev));
+	mgb_engine *e = new mgb_engine();
+	e->cfg = *cfg; e->cfg.nranks = P;
+	e->P = P; e->L = cfg->levels;
+	int rc = build_geometry(&e->cfg, e->geo, &e->La);
+	if (rc) { delete e; return rc; }
+	e->lay.resize(P);
+	for (int r = 0; r < P; ++r) build_layout(&e->cfg, e->geo, e->La, r, e->lay[r]);
+	const int nlocal = (P > 1 && cfg->emulate) ? P : 1;
+	e->strips.resize(nlocal);
+	for (int i = 0; i < nlocal; ++i) {
+		Strip &s = e->strips[i];
+		s.rank = nlocal > 1 ? i : cfg->rank;
+		s.device = dev;
+		const Layout &y = e->lay[s.rank];
+		if (i == 0) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+		else s.stream = e->strips[0].stream;                       // emulation: one stream, lock step
+		CU(cudaEventCreate(&s.ev0)); CU(cudaEventCreate(&s.ev1));
+		CU(cudaMalloc(&s.arena, y.total));
+		CU(cudaMemsetAsync(s.arena, 0, y.total, s.stream));
+		e->arena_of[s.rank] = s.arena;
+		s.lev.resize(e->L);
+		size_t nb = 3 * (size_t)MGB_RED_MAXBLOCKS;                 // partial sums: >= the largest streaming grid of the strip
+		for (int l = 0; l < e->L; ++l) {
+			SLevel &S = s.lev[l];
+			const LevelGeom &g = e->geo[l];
+			S.ni = y.ni[l]; S.r0 = y.r0[l];
+			S.present = y.vec_off[l][0] != NOOFF;
+			S.active = g.dist || s.rank == 0;
+			for (int k = 0; k < MGB_NVEC; ++k) {
+				S.phys[k] = k;
+				if (y.vec_off[l][k] == NOOFF) continue;
+				S.base[k] = (double *)(s.arena + y.vec_off[l][k]);
+				S.v[k] = S.base[k] + y.origin[l];
+			}
+			if (S.present) CU(cudaMalloc(&S.coef, sizeof(double) * g.coef_host.size()));
+			const size_t blocks = (size_t)cdiv(g.pitch, MGB_SB_COLS) * (size_t)(S.ni / 2 + 1);
+			if (blocks > nb) nb = blocks;
+		}
+		s.partial_cap = nb;
+		CU(cudaMalloc(&s.partial, sizeof(double) * nb));
+		CU(cudaMalloc(&s.scal, sizeof(double) * 64));
+		CU(cudaMemsetAsync(s.scal, 0, sizeof(double) * 64, s.stream));
+		CU(cudaMallocHost(&s.scal_host, sizeof(double) * 64));
+		CU(cudaMallocHost(&s.status_host, sizeof(int) * 4));
+		s.status_host[0] = 0;
+		CU(cudaMalloc(&s.tab_x, sizeof(double) * (size_t)(cfg->nj + 16)));
+		CU(cudaMalloc(&s.tab_y, sizeof(double) * (size_t)(cfg->ni + 16)));
+	}
+	CU(cudaStreamSynchronize(e->strips[0].stream));
+	e->connected = (P == 1) || nlocal > 1;
+	*out = e;
+	return MGB_OK;
+}
+
+extern "C" int mgb_ipc_export(mgb_engine *e, void *handle)
+{
+	if (!e || !handle) return fail(MGB_EINVAL, "null argument");
+	if (e->strips.size() != 1) return fail(MGB_ESTATE, "mgb_ipc_export is for one-strip-per-process engines");
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, e->strips[0].arena));
+	static_assert(sizeof(cudaIpcMemHandle_t) == MGB_IPC_HANDLE_BYTES, "IPC handle size");
+	memcpy(handle, &h, sizeof h);
+	return MGB_OK;
+}
+
+extern "C" int mgb_ipc_connect(mgb_engine *e, const void *handles)
+{
+	if (!e || !handles) return fail(MGB_EINVAL, "null argument");
+	if (e->P == 1 || e->strips.size() != 1) return fail(MGB_ESTATE, "mgb_ipc_connect is for one-strip-per-process engines with nranks > 1");
+	if (e->connected) return MGB_OK;
+	const int me = e->strips[0].rank;
+	for (int r = 0; r < e->P; ++r) {
+		if (r == me) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *)handles + (size_t)r * MGB_IPC_HANDLE_BYTES, sizeof h);
+		void *p = nullptr;
+		CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		e->arena_of[r] = (char *)p;
+		e->peer_opened[r] = true;
+	}
+	e->connected = true;
 	return MGB_OK;
 }
 
 extern "C" int mgb_level_dims(const mgb_engine *e, int level, int *ni, int *nj)
 {
-	if (!e || level < 0 || level >= (int)e->lev.size()) return fail(MGB_EINVAL, "level out of range");
-	if (ni) *ni = e->lev[level].ni;
-	if (nj) *nj = e->lev[level].nj;
+	if (!e || level < 0 || level >= e->L) return fail(MGB_EINVAL, "level out of range");
+	if (ni) *ni = e->geo[level].gni;
+	if (nj) *nj = e->geo[level].nj;
+	return MGB_OK;
+}
+// rows of level `level` that this process holds and computes ([0, n) on a single rank or in emulation)
+extern "C" int mgb_local_rows(const mgb_engine *e, int level, int *row0, int *row1)
+{
+	if (!e || level < 0 || level >= e->L) return fail(MGB_EINVAL, "level out of range");
+	int a = 0, b = e->geo[level].gni;
+	if (e->strips.size() == 1 && e->P > 1) {
+		const SLevel &S = e->strips[0].lev[level];
+		if (e->geo[level].dist) { a = S.r0; b = S.r0 + S.ni; }
+		else if (e->strips[0].rank != 0) { a = 0; b = 0; }
+	}
+	if (row0) *row0 = a;
+	if (row1) *row1 = b;
 	return MGB_OK;
 }
 extern "C" long long mgb_launch_count(const mgb_engine *e) { return e ? e->launches : 0; }
 extern "C" double mgb_last_solve_ms(const mgb_engine *e) { return e ? e->last_solve_ms : 0.0; }
 
-// ------------------------------------------------------------------------------------------------ operators
-static int upload_coef(mgb_engine *e, Level &L)
+static int sync_all(mgb_engine *e)
 {
-	CU(cudaMemcpyAsync(L.coef, L.coef_host.data(), sizeof(double) * L.coef_host.size(), cudaMemcpyHostToDevice, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
+	for (auto &s : e->strips) CU(cudaStreamSynchronize(s.stream));
 	return MGB_OK;
 }
+// after a synchronisation: did a halo wait time out?
+static int check_status(mgb_engine *e)
+{
+	if (e->P == 1) return MGB_OK;
+	for (auto &s : e->strips) {
+		CU(cudaMemcpyAsync(s.status_host, status_of(e, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+		if (s.status_host[0] != 0)
+			return fail(MGB_ECUDA, "rank %d: timed out waiting for a neighbour's ghost rows (a peer stopped or the ranks diverged)", s.rank);
+	}
+	return MGB_OK;
+}
+static int sync(mgb_engine *e) { TRY(sync_all(e)); return check_status(e); }
 
+// ------------------------------------------------------------------------------------------------ operators
 extern "C" int mgb_set_level_operator(mgb_engine *e, int level, const double *row_coeff)
 {
 	if (!e || !row_coeff) return fail(MGB_EINVAL, "null argument");
-	if (level < 0 || level >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d out of range", level);
-	Level &L = e->lev[level];
-	L.uniform = 1;
-	for (int i = 0; i < L.ni; ++i) {
-		double *c = &L.coef_host[(size_t)i * MGB_COEF_STRIDE];
+	if (level < 0 || level >= e->L) return fail(MGB_EINVAL, "level %d out of range", level);
+	LevelGeom &g = e->geo[level];
+	g.uniform = 1;
+	for (int i = 0; i < g.gni; ++i) {
+		double *c = &g.coef_host[(size_t)i * MGB_COEF_STRIDE];
 		for (int k = 0; k < 5; ++k) c[k] = row_coeff[i * 5 + k];
 		if (c[2] == 0.0) return fail(MGB_EINVAL, "zero diagonal on level %d grid row %d", level, i);
 		c[5] = 1.0 / c[2];          // PCSetUp_Jacobi: reciprocal of the diagonal
 		c[6] = 1.0 / c[2];          // MatInvertDiagonal_SeqAIJ with omega == 1
 		c[7] = c[2];                // mdiag
-		if (memcmp(c, &L.coef_host[0], 5 * sizeof(double)) != 0) L.uniform = 0;
+		if (memcmp(c, &g.coef_host[0], 5 * sizeof(double)) != 0) g.uniform = 0;
 	}
-	L.coef_set = true;
-	bandlu_free(L.lu);
+	g.coef_set = true;
 	e->sor_omega = 1.0;
 	e->csr_built = false;
-	return upload_coef(e, L);
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[level];
+		bandlu_free(S.lu);
+		if (!S.present) continue;
+		CU(cudaMemcpyAsync(S.coef, g.coef_host.data(), sizeof(double) * g.coef_host.size(), cudaMemcpyHostToDevice, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+	}
+	return MGB_OK;
 }
 
 // idiag = omega / diag for the SOR kernels (MatInvertDiagonal_SeqAIJ: 1/d when omega == 1 and fshift == 0)
 static int set_sor_omega(mgb_engine *e, double omega)
 {
 	if (e->sor_omega == omega) return MGB_OK;
-	for (auto &L : e->lev) {
-		for (int i = 0; i < L.ni; ++i) {
-			double *c = &L.coef_host[(size_t)i * MGB_COEF_STRIDE];
+	for (int l = 0; l < e->L; ++l) {
+		LevelGeom &g = e->geo[l];
+		for (int i = 0; i < g.gni; ++i) {
+			double *c = &g.coef_host[(size_t)i * MGB_COEF_STRIDE];
 			c[6] = (omega == 1.0) ? 1.0 / c[2] : omega / (0.0 + c[2]);
 		}
-		TRY(upload_coef(e, L));
+		for (auto &s : e->strips) {
+			if (!s.lev[l].present) continue;
+			CU(cudaMemcpyAsync(s.lev[l].coef, g.coef_host.data(), sizeof(double) * g.coef_host.size(), cudaMemcpyHostToDevice, s.stream));
+			CU(cudaStreamSynchronize(s.stream));
+		}
 	}
 	e->sor_omega = omega;
 	return MGB_OK;
@@ -243,13 +476,162 @@ extern "C" int mgb_set_transfer(mgb_engine *e, const double res3[9], const doubl
 static int require_ops(mgb_engine *e, bool transfer)
 {
 	if (!e) return fail(MGB_EINVAL, "null engine");
-	for (size_t l = 0; l < e->lev.size(); ++l)
-		if (!e->lev[l].coef_set) return fail(MGB_ESTATE, "mgb_set_level_operator was not called for level %d", (int)l);
-	if (transfer && e->lev.size() > 1 && !e->transfer_set) return fail(MGB_ESTATE, "mgb_set_transfer was not called");
+	for (int l = 0; l < e->L; ++l)
+		if (!e->geo[l].coef_set) return fail(MGB_ESTATE, "mgb_set_level_operator was not called for level %d", l);
+	if (transfer && e->L > 1 && !e->transfer_set) return fail(MGB_ESTATE, "mgb_set_transfer was not called");
+	return need_peers(e);
+}
+
+// ------------------------------------------------------------------------------------------------ strip-to-strip transfers
+static int xfer_blocks(unsigned long long total2)
+{
+	long long b = (long long)((total2 + MGB_XFER_THREADS * 4 - 1) / (MGB_XFER_THREADS * 4));
+	return (int)(b < 1 ? 1 : (b > 64 ? 64 : b));
+}
+// one process per strip: push + wait in one launch.  Emulation (all strips in this process, one GPU): the pushes of
+// every strip first, then the waits, so that no kernel ever waits for a kernel queued behind it.
+static int xfer_run(mgb_engine *e, std::vector<XferArgs> &args, const std::vector<unsigned long long> &tot, int chan)
+{
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i]; XferArgs &a = args[i];
+		a.ver = ver_of(e, s) + chan; a.ticket = ticket_of(e, s) + chan; a.status = status_of(e, s); a.spin_limit = e->spin_limit;
+		a.do_push = 1; a.do_wait = e->strips.size() == 1 ? 1 : 0;
+		k_xfer<<<xfer_blocks(tot[i]), MGB_XFER_THREADS, 0, s.stream>>>(a);
+		LAUNCHED(e); KCHECK();
+	}
+	if (e->strips.size() == 1) return MGB_OK;
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i]; XferArgs a = args[i];
+		a.do_push = 0; a.do_wait = 1;
+		k_xfer<<<1, 32, 0, s.stream>>>(a);
+		LAUNCHED(e); KCHECK();
+	}
 	return MGB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ CSR
+// ghost rows of vector `which` on distributed level l: `depth` boundary rows go to each neighbour
+static int halo(mgb_engine *e, int l, int which, int depth)
+{
+	if (e->P == 1 || !e->geo[l].dist) return MGB_OK;
+	const size_t pitch = e->geo[l].pitch;
+	std::vector<XferArgs> args(e->strips.size());
+	std::vector<unsigned long long> tot(e->strips.size(), 0);
+	int chan = 0;
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i]; SLevel &S = s.lev[l];
+		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
+		const int k = S.phys[which], r = s.rank;
+		chan = CH_HALO(l, k);
+		const unsigned long long cnt2 = (unsigned long long)depth * pitch / 2;
+		if (r > 0) {                                   // my first rows -> the lower ghost rows of rank r-1
+			const int d = a.ndst++;
+			a.src[d] = S.v[which];
+			a.dst[d] = peer_vec(e, r - 1, l, k) + (size_t)e->lay[r - 1].ni[l] * pitch;
+			a.cnt2[d] = cnt2;
+			a.peer_flag[d] = flags_of(e, r - 1) + (size_t)chan * MGB_MAX_RANKS + r;
+			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + (r - 1);
+		}
+		if (r < e->P - 1) {                            // my last rows -> the upper ghost rows of rank r+1
+			const int d = a.ndst++;
+			a.src[d] = S.v[which] + (size_t)(S.ni - depth) * pitch;
+			a.dst[d] = peer_vec(e, r + 1, l, k) - (size_t)depth * pitch;
+			a.cnt2[d] = cnt2;
+			a.peer_flag[d] = flags_of(e, r + 1) + (size_t)chan * MGB_MAX_RANKS + r;
+			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + (r + 1);
+		}
+		tot[i] = cnt2 * a.ndst;
+	}
+	return xfer_run(e, args, tot, chan);
+}
+
+// rows [rows[r], rows[r+1]) of vector `which` on the first agglomerated level: every rank -> rank 0
+static int gather_rows(mgb_engine *e, int l, int which)
+{
+	if (e->P == 1) return MGB_OK;
+	const size_t pitch = e->geo[l].pitch;
+	const int chan = CH_GATHER(l);
+	std::vector<XferArgs> args(e->strips.size());
+	std::vector<unsigned long long> tot(e->strips.size(), 0);
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i]; SLevel &S = s.lev[l];
+		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
+		const int r = s.rank, k = S.phys[which];
+		if (r != 0) {
+			const int c0 = e->geo[l].rows[r], c1 = e->geo[l].rows[r + 1];
+			a.ndst = 1;
+			a.src[0] = S.v[which] + (size_t)c0 * pitch;
+			a.dst[0] = peer_vec(e, 0, l, k) + (size_t)c0 * pitch;
+			a.cnt2[0] = (unsigned long long)(c1 - c0) * pitch / 2;
+			a.peer_flag[0] = flags_of(e, 0) + (size_t)chan * MGB_MAX_RANKS + r;
+			tot[i] = a.cnt2[0];
+		} else {
+			for (int q = 1; q < e->P; ++q) a.wait_flag[a.nwait++] = flags_of(e, 0) + (size_t)chan * MGB_MAX_RANKS + q;
+		}
+	}
+	return xfer_run(e, args, tot, chan);
+}
+
+// rows [rows[r]-1, rows[r+1]] of vector `which` on the first agglomerated level: rank 0 -> every rank
+static int bcast_rows(mgb_engine *e, int l, int which)
+{
+	if (e->P == 1) return MGB_OK;
+	const size_t pitch = e->geo[l].pitch;
+	const int chan = CH_BCAST(l);
+	std::vector<XferArgs> args(e->strips.size());
+	std::vector<unsigned long long> tot(e->strips.size(), 0);
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i]; SLevel &S = s.lev[l];
+		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
+		const int r = s.rank, k = S.phys[which];
+		if (r == 0) {
+			for (int q = 1; q < e->P; ++q) {
+				int c0 = e->geo[l].rows[q] - 1, c1 = e->geo[l].rows[q + 1] + 1;
+				if (c0 < 0) c0 = 0;
+				if (c1 > e->geo[l].gni) c1 = e->geo[l].gni;
+				const int d = a.ndst++;
+				a.src[d] = S.v[which] + (size_t)c0 * pitch;
+				a.dst[d] = peer_vec(e, q, l, k) + (size_t)c0 * pitch;
+				a.cnt2[d] = (unsigned long long)(c1 - c0) * pitch / 2;
+				a.peer_flag[d] = flags_of(e, q) + (size_t)chan * MGB_MAX_RANKS + 0;
+				tot[i] += a.cnt2[d];
+			}
+		} else {
+			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + 0;
+		}
+	}
+	return xfer_run(e, args, tot, chan);
+}
+
+// scal[SC_LOCAL .. SC_LOCAL+nvals) of every rank, summed in rank order into scal[slot ..) of every rank
+static int allreduce(mgb_engine *e, int nvals, int slot, int take_sqrt)
+{
+	const int chan = CH_REDUCE;
+	std::vector<XferArgs> args(e->strips.size());
+	std::vector<unsigned long long> tot(e->strips.size(), 1);
+	for (size_t i = 0; i < e->strips.size(); ++i) {
+		Strip &s = e->strips[i];
+		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
+		const int r = s.rank;
+		for (int q = 0; q < e->P; ++q) {
+			const int d = a.ndst++;
+			a.src[d] = s.scal + SC_LOCAL;
+			a.dst[d] = slots_of(e, q) + (size_t)r * RED_VALS;            // + parity offset, added in the kernel
+			a.cnt2[d] = RED_VALS / 2;
+			a.peer_flag[d] = flags_of(e, q) + (size_t)chan * MGB_MAX_RANKS + r;
+			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + q;
+		}
+		a.parity_stride = (unsigned long long)MGB_MAX_RANKS * RED_VALS;
+	}
+	TRY(xfer_run(e, args, tot, chan));
+	for (auto &s : e->strips) {
+		k_reduce_ranks<<<1, 32, 0, s.stream>>>(slots_of(e, s.rank), (unsigned long long)MGB_MAX_RANKS * RED_VALS, ver_of(e, s) + chan,
+		                                        e->P, nvals, s.scal, slot, take_sqrt);
+		LAUNCHED(e); KCHECK();
+	}
+	return MGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CSR (single rank)
 static int alloc_csr(Csr &c, int m, int n, long long nnz)
 {
 	free_csr(c);
@@ -273,30 +655,31 @@ extern "C" int mgb_assemble_csr(mgb_engine *e)
 	TRY(require_ops(e, true));
 	if (e->cfg.red_black_numbering)
 		return fail(MGB_EINVAL, "CSR assembly is offered for the reference's natural numbering only (-map 0,1,2), not the -map 3 extension");
-	const int Lc = (int)e->lev.size();
-	for (int l = 0; l < Lc; ++l) {
-		Level &L = e->lev[l];
-		const long long N = (long long)L.ni * L.nj;
+	if (e->P > 1) return fail(MGB_EINVAL, "CSR assembly runs on a single rank (the strips solve matrix-free)");
+	Strip &s = e->strips[0];
+	for (int l = 0; l < e->L; ++l) {
+		SLevel &S = s.lev[l]; const LevelGeom &g = e->geo[l];
+		const long long N = (long long)g.gni * g.nj;
 		if (N > 2147483647LL) return fail(MGB_EINVAL, "level %d has more rows than a 32-bit PetscInt holds", l);
-		const long long nnz = 5 * N - 2LL * L.ni - 2LL * L.nj;
-		TRY(alloc_csr(L.A, (int)N, (int)N, nnz));
-		dim3 g(cdiv(L.nj, 256), L.ni);
-		k_csr_A<<<g, 256, 0, e->stream>>>(L.A.rowptr, L.A.col, L.A.val, L.ni, L.nj, L.coef);
+		const long long nnz = 5 * N - 2LL * g.gni - 2LL * g.nj;
+		TRY(alloc_csr(S.A, (int)N, (int)N, nnz));
+		dim3 gr(cdiv(g.nj, 256), g.gni);
+		k_csr_A<<<gr, 256, 0, s.stream>>>(S.A.rowptr, S.A.col, S.A.val, g.gni, g.nj, S.coef);
 		LAUNCHED(e); KCHECK();
-		if (l + 1 < Lc) {
-			Level &C = e->lev[l + 1];
-			const long long NC = (long long)C.ni * C.nj;
-			TRY(alloc_csr(L.R, (int)NC, (int)N, 9 * NC));
-			dim3 gr(cdiv(C.nj, 256), C.ni);
-			k_csr_R<<<gr, 256, 0, e->stream>>>(L.R.rowptr, L.R.col, L.R.val, C.ni, C.nj, L.nj, e->R3);
+		if (l + 1 < e->L) {
+			const LevelGeom &c = e->geo[l + 1];
+			const long long NC = (long long)c.gni * c.nj;
+			TRY(alloc_csr(S.R, (int)NC, (int)N, 9 * NC));
+			dim3 grr(cdiv(c.nj, 256), c.gni);
+			k_csr_R<<<grr, 256, 0, s.stream>>>(S.R.rowptr, S.R.col, S.R.val, c.gni, c.nj, g.nj, e->R3);
 			LAUNCHED(e); KCHECK();
-			const long long pnnz = host_touch_prefix(L.ni, C.ni) * host_touch_prefix(L.nj, C.nj);
-			TRY(alloc_csr(L.P, (int)N, (int)NC, pnnz));
-			k_csr_P<<<g, 256, 0, e->stream>>>(L.P.rowptr, L.P.col, L.P.val, L.ni, L.nj, C.ni, C.nj, e->P3);
+			const long long pnnz = host_touch_prefix(g.gni, c.gni) * host_touch_prefix(g.nj, c.nj);
+			TRY(alloc_csr(S.P, (int)N, (int)NC, pnnz));
+			k_csr_P<<<gr, 256, 0, s.stream>>>(S.P.rowptr, S.P.col, S.P.val, g.gni, g.nj, c.gni, c.nj, e->P3);
 			LAUNCHED(e); KCHECK();
 		}
 	}
-	CU(cudaStreamSynchronize(e->stream));
+	CU(cudaStreamSynchronize(s.stream));
 	e->csr_built = true;
 	return MGB_OK;
 }
@@ -305,19 +688,19 @@ static int pick_csr(const mgb_engine *e, int which, int level, const Csr **out)
 {
 	if (!e) return fail(MGB_EINVAL, "null engine");
 	if (!e->csr_built) return fail(MGB_ESTATE, "mgb_assemble_csr was not called");
-	if (level < 0 || level >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d out of range", level);
-	const Level &L = e->lev[level];
-	if (which == MGB_MAT_A) *out = &L.A;
-	else if (level + 1 >= (int)e->lev.size()) return fail(MGB_EINVAL, "no transfer operator below the coarsest level");
-	else if (which == MGB_MAT_RES) *out = &L.R;
-	else if (which == MGB_MAT_PRO) *out = &L.P;
+	if (level < 0 || level >= e->L) return fail(MGB_EINVAL, "level %d out of range", level);
+	const SLevel &S = e->strips[0].lev[level];
+	if (which == MGB_MAT_A) *out = &S.A;
+	else if (level + 1 >= e->L) return fail(MGB_EINVAL, "no transfer operator below the coarsest level");
+	else if (which == MGB_MAT_RES) *out = &S.R;
+	else if (which == MGB_MAT_PRO) *out = &S.P;
 	else return fail(MGB_EINVAL, "matrix id %d out of range", which);
 	return MGB_OK;
 }
 
 extern "C" int mgb_csr_dims(const mgb_engine *e, int which, int level, int *m, int *n, long long *nnz)
 {
-	const Csr *c; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
 	if (m) *m = c->m;
 	if (n) *n = c->n;
 	if (nnz) *nnz = c->nnz;
@@ -326,7 +709,7 @@ extern "C" int mgb_csr_dims(const mgb_engine *e, int which, int level, int *m, i
 
 extern "C" int mgb_csr_get(const mgb_engine *e, int which, int level, int *rowptr, int *col, double *val)
 {
-	const Csr *c; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
 	if (rowptr) CU(cudaMemcpy(rowptr, c->rowptr, sizeof(int) * ((size_t)c->m + 1), cudaMemcpyDeviceToHost));
 	if (col) CU(cudaMemcpy(col, c->col, sizeof(int) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
 	if (val) CU(cudaMemcpy(val, c->val, sizeof(double) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
@@ -334,201 +717,274 @@ extern "C" int mgb_csr_get(const mgb_engine *e, int which, int level, int *rowpt
 }
 
 // ------------------------------------------------------------------------------------------------ vectors
+// Host vectors are whole-grid arrays (gni x nj, natural order).  Every local strip moves its own rows; in a
+// one-strip-per-process run the other rows of the host array are neither read nor written.
 extern "C" int mgb_vec_set(mgb_engine *e, int which, int level, const double *host)
 {
 	if (!e || !host) return fail(MGB_EINVAL, "null argument");
-	double *d; TRY(vec_ptr(e, which, level, &d));
-	Level &L = e->lev[level];
-	CU(cudaMemcpy2DAsync(d, sizeof(double) * L.pitch, host, sizeof(double) * L.nj, sizeof(double) * L.nj, L.ni,
-	                     cudaMemcpyHostToDevice, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
-	return MGB_OK;
+	TRY(check_vec(e, which, level));
+	const LevelGeom &g = e->geo[level];
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[level];
+		if (!S.present || !S.active) continue;
+		CU(cudaMemcpy2DAsync(S.v[which], sizeof(double) * g.pitch, host + (size_t)S.r0 * g.nj, sizeof(double) * g.nj,
+		                     sizeof(double) * g.nj, S.ni, cudaMemcpyHostToDevice, s.stream));
+	}
+	return sync_all(e);
 }
 extern "C" int mgb_vec_get(mgb_engine *e, int which, int level, double *host)
 {
 	if (!e || !host) return fail(MGB_EINVAL, "null argument");
-	double *d; TRY(vec_ptr(e, which, level, &d));
-	Level &L = e->lev[level];
-	CU(cudaMemcpy2DAsync(host, sizeof(double) * L.nj, d, sizeof(double) * L.pitch, sizeof(double) * L.nj, L.ni,
-	                     cudaMemcpyDeviceToHost, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
-	return MGB_OK;
+	TRY(check_vec(e, which, level));
+	const LevelGeom &g = e->geo[level];
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[level];
+		if (!S.present || !S.active) continue;
+		CU(cudaMemcpy2DAsync(host + (size_t)S.r0 * g.nj, sizeof(double) * g.nj, S.v[which], sizeof(double) * g.pitch,
+		                     sizeof(double) * g.nj, S.ni, cudaMemcpyDeviceToHost, s.stream));
+	}
+	return sync_all(e);
 }
+// zero the own rows AND the ghost rows (the neighbours zero theirs in the same step, so no exchange is needed)
 static int vec_zero(mgb_engine *e, int which, int level)
 {
-	double *d; TRY(vec_ptr(e, which, level, &d));
-	Level &L = e->lev[level];
-	const size_t n2 = (size_t)L.ni * L.pitch / 2;
-	const int blocks = (int)((n2 + 255) / 256 < 2368 ? (n2 + 255) / 256 : 2368);
-	k_axpy<3><<<blocks, 256, 0, e->stream>>>(d, nullptr, n2, 0.0, nullptr, 0.0);
-	LAUNCHED(e); KCHECK();
+	TRY(check_vec(e, which, level));
+	const LevelGeom &g = e->geo[level];
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[level];
+		if (!S.present || !S.active) continue;
+		const size_t n2 = (size_t)(S.ni + 2 * MGB_GHOST_ROWS) * g.pitch / 2;
+		const int blocks = (int)((n2 + 255) / 256 < 2368 ? (n2 + 255) / 256 : 2368);
+		k_axpy<3><<<blocks, 256, 0, s.stream>>>(S.v[which] - (size_t)MGB_GHOST_ROWS * g.pitch, nullptr, n2, 0.0, nullptr, 0.0);
+		LAUNCHED(e); KCHECK();
+	}
 	return MGB_OK;
 }
 extern "C" int mgb_vec_zero(mgb_engine *e, int which, int level)
 {
 	if (!e) return fail(MGB_EINVAL, "null engine");
 	TRY(vec_zero(e, which, level));
-	CU(cudaStreamSynchronize(e->stream));
-	return MGB_OK;
+	return sync(e);
 }
 extern "C" int mgb_set_rhs(mgb_engine *e, const double *b0) { return mgb_vec_set(e, MGB_VEC_B, 0, b0); }
 extern "C" int mgb_get_solution(mgb_engine *e, double *u0) { return mgb_vec_get(e, MGB_VEC_U, 0, u0); }
 
-static int upload_tables(mgb_engine *e, const double *tx, const double *ty)
-{
-	Level &L = e->lev[0];
-	CU(cudaMemcpyAsync(e->tab_x, tx, sizeof(double) * L.nj, cudaMemcpyHostToDevice, e->stream));
-	CU(cudaMemcpyAsync(e->tab_y, ty, sizeof(double) * L.ni, cudaMemcpyHostToDevice, e->stream));
-	return MGB_OK;
-}
 extern "C" int mgb_set_rhs_separable(mgb_engine *e, const double *gx, const double *gy)
 {
 	if (!e || !gx || !gy) return fail(MGB_EINVAL, "null argument");
-	double *b; TRY(vec_ptr(e, MGB_VEC_B, 0, &b));
-	TRY(upload_tables(e, gx, gy));
-	Level &L = e->lev[0];
-	dim3 g(cdiv(L.pitch, 256), L.ni);
-	k_outer<<<g, 256, 0, e->stream>>>(b, e->tab_x, e->tab_y, ldev(L));
-	LAUNCHED(e); KCHECK();
-	CU(cudaStreamSynchronize(e->stream));
-	return MGB_OK;
-}
-extern "C" int mgb_error_norms_separable(mgb_engine *e, const double *sx, const double *sy, double error[3])
-{
-	if (!e || !sx || !sy || !error) return fail(MGB_EINVAL, "null argument");
-	double *u; TRY(vec_ptr(e, MGB_VEC_U, 0, &u));
-	TRY(upload_tables(e, sx, sy));
-	Level &L = e->lev[0];
-	const size_t total = (size_t)L.ni * L.pitch;
-	const int blocks = (int)((total + MGB_RED_THREADS - 1) / MGB_RED_THREADS < 1184 ? (total + MGB_RED_THREADS - 1) / MGB_RED_THREADS : 1184);
-	k_error<<<blocks, MGB_RED_THREADS, 0, e->stream>>>(u, e->tab_x, e->tab_y, ldev(L), e->partial);
-	LAUNCHED(e); KCHECK();
-	k_error2<<<1, 32, 0, e->stream>>>(e->partial, blocks, e->scal + 8);
-	LAUNCHED(e); KCHECK();
-	CU(cudaMemcpyAsync(e->scal_host + 8, e->scal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
-	for (int k = 0; k < 3; ++k) error[k] = e->scal_host[8 + k];
-	return MGB_OK;
+	const LevelGeom &g = e->geo[0];
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[0];
+		CU(cudaMemcpyAsync(s.tab_x, gx, sizeof(double) * g.nj, cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemcpyAsync(s.tab_y, gy, sizeof(double) * g.gni, cudaMemcpyHostToDevice, s.stream));
+		dim3 gr(cdiv(g.pitch, 256), S.ni);
+		k_outer<<<gr, 256, 0, s.stream>>>(S.v[MGB_VEC_B], s.tab_x, s.tab_y, ldev(e, s, 0));
+		LAUNCHED(e); KCHECK();
+	}
+	return sync_all(e);
 }
 
 // ------------------------------------------------------------------------------------------------ launch helpers
-// All helpers enqueue on e->stream and do not synchronise.
+// All helpers enqueue on the strips' streams and do not synchronise.  They loop over the local strips that compute
+// on the level (every strip of a distributed level; rank 0 only on an agglomerated one).
+static inline bool computes(const Strip &s, int l) { return s.lev[l].present && s.lev[l].active; }
 
-static int k_apply(mgb_engine *e, int l, const double *x, double *y)
+// rows per block of the streaming kernels: 32 on large levels, fewer on small ones so that the grid still fills
+// the 148 SMs (>= ~1184 blocks when the level allows it)
+static int pick_ry(const LevelGeom &g, int ni)
 {
-	Level &L = e->lev[l];
-	k_stream5<ST_APPLY, RY_STREAM><<<stream_grid(L), MGB_SB_THREADS, 0, e->stream>>>(x, nullptr, y, ldev(L), 0.0, nullptr);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
+	const long long cb = cdiv(g.pitch, MGB_SB_COLS);
+	long long ry = (long long)ni * cb / 1184;
+	if (ry > 32) ry = 32;
+	if (ry < 2) ry = 2;
+	return (int)ry;
 }
-static int k_residual(mgb_engine *e, int l, const double *x, const double *b, double *r)
+static dim3 stream_grid(const LevelGeom &g, int ni, int ry) { return dim3(cdiv(g.pitch, MGB_SB_COLS), cdiv(ni, ry)); }
+
+static int k_apply(mgb_engine *e, int l, int xv, int yv)
 {
-	Level &L = e->lev[l];
-	k_stream5<ST_RESID, RY_STREAM><<<stream_grid(L), MGB_SB_THREADS, 0, e->stream>>>(x, b, r, ldev(L), 0.0, nullptr);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
-}
-// scal[slot] = || b - A x ||_2
-static int k_resnorm(mgb_engine *e, int l, const double *x, const double *b, int slot)
-{
-	Level &L = e->lev[l];
-	const dim3 g = stream_grid(L);
-	if ((size_t)g.x * g.y > e->partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
-	k_stream5<ST_RESNORM, RY_STREAM><<<g, MGB_SB_THREADS, 0, e->stream>>>(x, b, nullptr, ldev(L), 0.0, e->partial);
-	LAUNCHED(e); KCHECK();
-	k_reduce2<<<1, 1024, 0, e->stream>>>(e->partial, (int)(g.x * g.y), e->scal, slot, 1);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
-}
-static int k_reduce(mgb_engine *e, int l, const double *x, const double *y, int slot, int take_sqrt)
-{
-	Level &L = e->lev[l];
-	const size_t n2 = (size_t)L.ni * L.pitch / 2;
-	size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
-	const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
-	if (y) k_reduce1<1><<<blocks, MGB_RED_THREADS, 0, e->stream>>>(x, y, n2, e->partial);
-	else   k_reduce1<0><<<blocks, MGB_RED_THREADS, 0, e->stream>>>(x, nullptr, n2, e->partial);
-	LAUNCHED(e); KCHECK();
-	k_reduce2<<<1, 1024, 0, e->stream>>>(e->partial, blocks, e->scal, slot, take_sqrt);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
-}
-template <int KIND>
-static int k_vecop(mgb_engine *e, int l, double *y, const double *x, double alpha)
-{
-	Level &L = e->lev[l];
-	const size_t n2 = (size_t)L.ni * L.pitch / 2;
-	size_t want = (n2 + 255) / 256;
-	const int blocks = (int)(want < 1 ? 1 : (want > 148 * 32 ? 148 * 32 : want));
-	k_axpy<KIND><<<blocks, 256, 0, e->stream>>>(y, x, n2, alpha, nullptr, 0.0);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
-}
-static int read_scalars(mgb_engine *e, int first, int count)
-{
-	CU(cudaMemcpyAsync(e->scal_host + first, e->scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
+	const LevelGeom &g = e->geo[l];
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const int ry = pick_ry(g, S.ni);
+		k_stream5<ST_APPLY><<<stream_grid(g, S.ni, ry), MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], nullptr, S.v[yv], ldev(e, s, l), 0.0, nullptr, ry);
+		LAUNCHED(e); KCHECK();
+	}
 	return MGB_OK;
 }
-
-// one red-black half sweep of colour c (0 = red: (i+j) even), in place
-static int k_rb(mgb_engine *e, int l, double *x, const double *b, int colour, double omega, int variant)
+static int k_residual(mgb_engine *e, int l, int xv, int bv, int rv)
 {
-	Level &L = e->lev[l];
-	if (variant == 0) k_rb_half<0, RY_STREAM><<<stream_grid(L), MGB_SB_THREADS, 0, e->stream>>>(x, b, ldev(L), colour, omega);
-	else              k_rb_half<1, RY_STREAM><<<stream_grid(L), MGB_SB_THREADS, 0, e->stream>>>(x, b, ldev(L), colour, omega);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
+	const LevelGeom &g = e->geo[l];
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const int ry = pick_ry(g, S.ni);
+		k_stream5<ST_RESID><<<stream_grid(g, S.ni, ry), MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], S.v[rv], ldev(e, s, l), 0.0, nullptr, ry);
+		LAUNCHED(e); KCHECK();
+	}
+	return MGB_OK;
+}
+// final stage of a reduction: local partials -> scal[slot] (single rank) or -> all-reduce over the ranks
+static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, int slot, int take_sqrt)
+{
+	const bool global = e->P > 1 && e->geo[l].dist;
+	size_t i = 0;
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		k_reduce2<<<1, 1024, 0, s.stream>>>(s.partial, nblocks[i++], s.scal, global ? SC_LOCAL : slot, global ? 0 : take_sqrt);
+		LAUNCHED(e); KCHECK();
+	}
+	if (global) TRY(allreduce(e, 1, slot, take_sqrt));
+	return MGB_OK;
+}
+// scal[slot] = || b - A x ||_2
+static int k_resnorm(mgb_engine *e, int l, int xv, int bv, int slot)
+{
+	const LevelGeom &g = e->geo[l];
+	std::vector<int> nb;
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const int ry = pick_ry(g, S.ni);
+		const dim3 gr = stream_grid(g, S.ni, ry);
+		if ((size_t)gr.x * gr.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
+		k_stream5<ST_RESNORM><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], nullptr, ldev(e, s, l), 0.0, s.partial, ry);
+		LAUNCHED(e); KCHECK();
+		nb.push_back((int)(gr.x * gr.y));
+	}
+	return reduce_tail(e, l, nb, slot, 1);
+}
+// scal[slot] = sqrt?(sum x*y) (yv < 0: sum x*x)
+static int k_reduce(mgb_engine *e, int l, int xv, int yv, int slot, int take_sqrt)
+{
+	const LevelGeom &g = e->geo[l];
+	std::vector<int> nb;
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const size_t n2 = (size_t)S.ni * g.pitch / 2;
+		size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
+		const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
+		if (yv >= 0) k_reduce1<1><<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], S.v[yv], n2, s.partial);
+		else         k_reduce1<0><<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], nullptr, n2, s.partial);
+		LAUNCHED(e); KCHECK();
+		nb.push_back(blocks);
+	}
+	return reduce_tail(e, l, nb, slot, take_sqrt);
+}
+template <int KIND>
+static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha)
+{
+	const LevelGeom &g = e->geo[l];
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const size_t n2 = (size_t)S.ni * g.pitch / 2;
+		size_t want = (n2 + 255) / 256;
+		const int blocks = (int)(want < 1 ? 1 : (want > 148 * 32 ? 148 * 32 : want));
+		k_axpy<KIND><<<blocks, 256, 0, s.stream>>>(S.v[yv], S.v[xv], n2, alpha, nullptr, 0.0);
+		LAUNCHED(e); KCHECK();
+	}
+	return MGB_OK;
+}
+// scal[first .. first+count) of the first local strip -> its pinned mirror (every rank holds identical values)
+static int read_scalars(mgb_engine *e, int first, int count)
+{
+	Strip &s = e->strips[0];
+	CU(cudaMemcpyAsync(s.scal_host + first, s.scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, s.stream));
+	CU(cudaStreamSynchronize(s.stream));
+	return MGB_OK;
+}
+static double *host_scal(mgb_engine *e) { return e->strips[0].scal_host; }
+
+// one red-black half sweep of colour c (0 = red: (i+j) even), in place; ghost rows valid on return
+static int k_rb(mgb_engine *e, int l, int xv, int bv, int colour, double omega, int variant)
+{
+	const LevelGeom &g = e->geo[l];
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const int ry = pick_ry(g, S.ni);
+		const dim3 gr = stream_grid(g, S.ni, ry);
+		if (variant == 0) k_rb_half<0><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], ldev(e, s, l), colour, omega, ry);
+		else              k_rb_half<1><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], ldev(e, s, l), colour, omega, ry);
+		LAUNCHED(e); KCHECK();
+	}
+	return halo(e, l, xv, 2);
+}
+
+static void swap_vec(mgb_engine *e, int l, int a, int b)
+{
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[l];
+		double *t = S.v[a]; S.v[a] = S.v[b]; S.v[b] = t;
+		int p = S.phys[a]; S.phys[a] = S.phys[b]; S.phys[b] = p;
+	}
 }
 
 // The level smoother: KSPSolve(KSPRICHARDSON, KSP_NORM_NONE, max_it = its) on (b, x) -- exactly `its`
 // iterations, no convergence test (ref: src/solver.c:1463-1510; semantics in SURVEY.md appendix A).
 // xv / sv: vector ids of the iterate and of the Jacobi ping-pong scratch; on return the iterate is in v[xv]
-// (the two device pointers are swapped when the sweep count is odd).
-static int smooth(mgb_engine *e, int l, const mgb_smoother *s, int its, bool guess_zero, int bv, int xv, int sv)
+// (the two device pointers are swapped after every out-of-place sweep) and its ghost rows are valid (depth 2).
+static int smooth(mgb_engine *e, int l, const mgb_smoother *sm, int its, bool guess_zero, int bv, int xv, int sv)
 {
-	Level &L = e->lev[l];
-	double *b, *x, *w;
-	TRY(vec_ptr(e, bv, l, &b)); TRY(vec_ptr(e, xv, l, &x)); TRY(vec_ptr(e, sv, l, &w));
-	if (s->type == MGB_SMOOTH_JACOBI) {
+	const LevelGeom &g = e->geo[l];
+	if (sm->type == MGB_SMOOTH_JACOBI) {
 		int k = 0;
 		if (guess_zero) {
 			if (its <= 0) return vec_zero(e, xv, l);
-			dim3 g(cdiv(L.pitch, 512), L.ni);
-			k_jacobi_first<<<g, 256, 0, e->stream>>>(b, x, ldev(L), s->scale);
-			LAUNCHED(e); KCHECK();
+			for (auto &s : e->strips) {
+				if (!computes(s, l)) continue;
+				SLevel &S = s.lev[l];
+				dim3 gr(cdiv(g.pitch, 512), S.ni);
+				k_jacobi_first<<<gr, 256, 0, s.stream>>>(S.v[bv], S.v[xv], ldev(e, s, l), sm->scale);
+				LAUNCHED(e); KCHECK();
+			}
+			TRY(halo(e, l, xv, 2));
 			k = 1;
 		}
 		for (; k < its; ++k) {
-			k_stream5<ST_JACOBI, RY_STREAM><<<stream_grid(L), MGB_SB_THREADS, 0, e->stream>>>(x, b, w, ldev(L), s->scale, nullptr);
-			LAUNCHED(e); KCHECK();
-			double *t = x; x = w; w = t;
+			for (auto &s : e->strips) {
+				if (!computes(s, l)) continue;
+				SLevel &S = s.lev[l];
+				const int ry = pick_ry(g, S.ni);
+				k_stream5<ST_JACOBI><<<stream_grid(g, S.ni, ry), MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], S.v[sv], ldev(e, s, l), sm->scale, nullptr, ry);
+				LAUNCHED(e); KCHECK();
+			}
+			swap_vec(e, l, xv, sv);
+			TRY(halo(e, l, xv, 2));
 		}
-		L.v[xv] = x; L.v[sv] = w;
 		return MGB_OK;
 	}
-	if (s->type == MGB_SMOOTH_RBSOR) {
+	if (sm->type == MGB_SMOOTH_RBSOR) {
 		// KSPSolve_Richardson hands the whole loop to PCApplyRichardson_SOR only when scale == 1:
 		// MatSOR(its * pc_its * lits sweeps).  Other scales go through PCApply_SOR per iteration: not offered.
-		if (s->scale != 1.0) return fail(MGB_EINVAL, "red-black SOR needs -ksp_richardson_scale 1 (PCApplyRichardson_SOR path)");
+		if (sm->scale != 1.0) return fail(MGB_EINVAL, "red-black SOR needs -ksp_richardson_scale 1 (PCApplyRichardson_SOR path)");
 		if (guess_zero) TRY(vec_zero(e, xv, l));
-		const int total = its * (s->sor_its > 0 ? s->sor_its : 1);
-		const double om = s->omega;
+		const int total = its * (sm->sor_its > 0 ? sm->sor_its : 1);
+		const double om = sm->omega;
 		for (int k = 0; k < total; ++k) {
-			if (s->sor_sweep == MGB_SOR_SYMMETRIC) {
+			if (sm->sor_sweep == MGB_SOR_SYMMETRIC) {
 				// forward: red, black ; backward: black (no-op when omega == 1: x = t * idiag again), red.
 				// A red half sweep directly after a red half sweep recomputes the same values when omega == 1.
 				const bool prev_red = (k > 0);
-				if (!(prev_red && om == 1.0)) TRY(k_rb(e, l, x, b, 0, om, 0));
-				TRY(k_rb(e, l, x, b, 1, om, 0));
-				if (om != 1.0) TRY(k_rb(e, l, x, b, 1, om, 0));
-				TRY(k_rb(e, l, x, b, 0, om, 0));
-			} else if (s->sor_sweep == MGB_SOR_FORWARD) {
-				TRY(k_rb(e, l, x, b, 0, om, 0));
-				TRY(k_rb(e, l, x, b, 1, om, 0));
-			} else if (s->sor_sweep == MGB_SOR_BACKWARD) {
+				if (!(prev_red && om == 1.0)) TRY(k_rb(e, l, xv, bv, 0, om, 0));
+				TRY(k_rb(e, l, xv, bv, 1, om, 0));
+				if (om != 1.0) TRY(k_rb(e, l, xv, bv, 1, om, 0));
+				TRY(k_rb(e, l, xv, bv, 0, om, 0));
+			} else if (sm->sor_sweep == MGB_SOR_FORWARD) {
+				TRY(k_rb(e, l, xv, bv, 0, om, 0));
+				TRY(k_rb(e, l, xv, bv, 1, om, 0));
+			} else if (sm->sor_sweep == MGB_SOR_BACKWARD) {
 				const int variant = (guess_zero && k == 0) ? 0 : 1;
-				TRY(k_rb(e, l, x, b, 1, om, variant));
-				TRY(k_rb(e, l, x, b, 0, om, variant));
-			} else return fail(MGB_EINVAL, "unknown sor_sweep %d", s->sor_sweep);
+				TRY(k_rb(e, l, xv, bv, 1, om, variant));
+				TRY(k_rb(e, l, xv, bv, 0, om, variant));
+			} else return fail(MGB_EINVAL, "unknown sor_sweep %d", sm->sor_sweep);
 		}
 		return MGB_OK;
 	}
-	return fail(MGB_EINVAL, "unknown smoother type %d", s->type);
+	return fail(MGB_EINVAL, "unknown smoother type %d", sm->type);
 }
 
 static int check_smoother(mgb_engine *e, const mgb_smoother *s)
@@ -541,132 +997,185 @@ static int check_smoother(mgb_engine *e, const mgb_smoother *s)
 	return MGB_OK;
 }
 
-// b[l+1] = res[l] * (b[l] - A[l] x[l])   fused (ref: src/solver.c:1534-1535)
-static int restrict_fused(mgb_engine *e, int l, int bv, int xv)
+// the coarse level as a strip sees it in a transfer from / to the distributed level above: its own strip of a
+// distributed coarse level, or its rows [rows[r], rows[r+1]) of the whole first agglomerated level
+static LevelDev coarse_view(const mgb_engine *e, const Strip &s, int lc, bool fine_dist, size_t *row_off)
 {
-	Level &F = e->lev[l], &C = e->lev[l + 1];
-	double *b, *x, *bc;
-	TRY(vec_ptr(e, bv, l, &b)); TRY(vec_ptr(e, xv, l, &x)); TRY(vec_ptr(e, MGB_VEC_B, l + 1, &bc));
-	dim3 blk(32, 4), g(cdiv(C.pitch, 32), cdiv(C.ni, 4));
-	k_restrict<1><<<g, blk, 0, e->stream>>>(x, b, nullptr, bc, ldev(F), ldev(C), e->R3);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
+	const LevelGeom &gc = e->geo[lc];
+	*row_off = 0;
+	if (gc.dist || e->P == 1 || !fine_dist) return ldev(e, s, lc);
+	*row_off = (size_t)gc.rows[s.rank] * gc.pitch;
+	return ldev_rows(e, s, lc, gc.rows[s.rank], gc.rows[s.rank + 1]);
 }
-// x[l] += pro[l] * u[l+1]   (ref: src/solver.c:1540-1541 ; PCMG: MatInterpolateAdd)
+
+// b[l+1] = res[l] * (fused ? bv[l] - A[l] xv[l] : rv[l])   (ref: src/solver.c:1534-1535).  Every strip of a
+// distributed level produces its own coarse rows; when the coarse level is the first agglomerated one they are
+// gathered on rank 0, otherwise the coarse ghost rows are exchanged.  Needs ghost depth 2 of xv and 1 of bv / rv.
+static int restrict_to_coarse(mgb_engine *e, int l, int bv, int xv, int rv, bool fused)
+{
+	const LevelGeom &gf = e->geo[l], &gc = e->geo[l + 1];
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &F = s.lev[l], &C = s.lev[l + 1];
+		size_t coff; const LevelDev cd = coarse_view(e, s, l + 1, gf.dist, &coff);
+		dim3 blk(32, 4), gr(cdiv(gc.pitch, 32), cdiv(cd.ni, 4));
+		double *bc = C.v[MGB_VEC_B] + coff;
+		if (fused) k_restrict<1><<<gr, blk, 0, s.stream>>>(F.v[xv], F.v[bv], nullptr, bc, ldev(e, s, l), cd, e->R3);
+		else       k_restrict<0><<<gr, blk, 0, s.stream>>>(nullptr, nullptr, F.v[rv], bc, ldev(e, s, l), cd, e->R3);
+		LAUNCHED(e); KCHECK();
+	}
+	if (gc.dist) return halo(e, l + 1, MGB_VEC_B, 2);
+	if (gf.dist) return gather_rows(e, l + 1, MGB_VEC_B);
+	return MGB_OK;
+}
+// x[l] += pro[l] * u[l+1]   (ref: src/solver.c:1540-1541 ; PCMG: MatInterpolateAdd); ghost rows of x valid on return
 static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 {
-	Level &F = e->lev[l], &C = e->lev[l + 1];
-	double *x, *uc;
-	TRY(vec_ptr(e, xv, l, &x)); TRY(vec_ptr(e, MGB_VEC_U, l + 1, &uc));
-	dim3 blk(32, 4), g(cdiv(F.pitch, 64), cdiv(F.ni, 4));
-	if (multadd) k_prolong_add<1><<<g, blk, 0, e->stream>>>(x, uc, ldev(F), ldev(C), e->P3);
-	else         k_prolong_add<0><<<g, blk, 0, e->stream>>>(x, uc, ldev(F), ldev(C), e->P3);
-	LAUNCHED(e); KCHECK(); return MGB_OK;
+	const LevelGeom &gf = e->geo[l], &gc = e->geo[l + 1];
+	if (gf.dist && !gc.dist) TRY(bcast_rows(e, l + 1, MGB_VEC_U));
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &F = s.lev[l], &C = s.lev[l + 1];
+		size_t coff; const LevelDev cd = coarse_view(e, s, l + 1, gf.dist, &coff);
+		dim3 blk(32, 4), gr(cdiv(gf.pitch, 64), cdiv(F.ni, 4));
+		const double *uc = C.v[MGB_VEC_U] + coff;
+		if (multadd) k_prolong_add<1><<<gr, blk, 0, s.stream>>>(F.v[xv], uc, ldev(e, s, l), cd, e->P3);
+		else         k_prolong_add<0><<<gr, blk, 0, s.stream>>>(F.v[xv], uc, ldev(e, s, l), cd, e->P3);
+		LAUNCHED(e); KCHECK();
+	}
+	return halo(e, l, xv, 2);
 }
 
 // ------------------------------------------------------------------------------------------------ single ops (C-ABI)
+// The single operations are collective in a multi-rank run.  They refresh the ghost rows of their inputs first
+// (vectors may have been set from the host); the solvers keep ghosts valid incrementally.
 #define NEED(e) do { if (!(e)) return fail(MGB_EINVAL, "null engine"); } while (0)
-static int sync(mgb_engine *e) { CU(cudaStreamSynchronize(e->stream)); return MGB_OK; }
+#define GHOSTS(e, l, which) TRY(halo(e, l, which, 2))
+
+extern "C" int mgb_error_norms_separable(mgb_engine *e, const double *sx, const double *sy, double error[3])
+{
+	if (!e || !sx || !sy || !error) return fail(MGB_EINVAL, "null argument");
+	if (e->P > 1 && e->strips.size() == 1)
+		return fail(MGB_EINVAL, "error norms of a multi-process run are combined by the caller from the per-rank rows");
+	const LevelGeom &g = e->geo[0];
+	const bool multi = e->strips.size() > 1;
+	double mx = 0.0, s1 = 0.0, s2 = 0.0;
+	for (auto &s : e->strips) {
+		SLevel &S = s.lev[0];
+		CU(cudaMemcpyAsync(s.tab_x, sx, sizeof(double) * g.nj, cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemcpyAsync(s.tab_y, sy, sizeof(double) * g.gni, cudaMemcpyHostToDevice, s.stream));
+		const size_t total = (size_t)S.ni * g.pitch;
+		const int blocks = (int)((total + MGB_RED_THREADS - 1) / MGB_RED_THREADS < 1184 ? (total + MGB_RED_THREADS - 1) / MGB_RED_THREADS : 1184);
+		k_error<<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[MGB_VEC_U], s.tab_x, s.tab_y, ldev(e, s, 0), s.partial);
+		LAUNCHED(e); KCHECK();
+		k_error2<<<1, 32, 0, s.stream>>>(s.partial, blocks, s.scal + 8, multi ? 0 : 1);
+		LAUNCHED(e); KCHECK();
+		CU(cudaMemcpyAsync(s.scal_host + 8, s.scal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+		mx = fmax(mx, s.scal_host[8]); s1 += s.scal_host[9]; s2 += s.scal_host[10];
+	}
+	error[0] = mx; error[1] = s1; error[2] = multi ? sqrt(s2) : s2;
+	return MGB_OK;
+}
 
 extern "C" int mgb_op_apply(mgb_engine *e, int level, int x_vec, int y_vec)
 {
-	NEED(e); TRY(require_ops(e, false));
+	NEED(e); TRY(require_ops(e, false)); TRY(check_vec(e, x_vec, level)); TRY(check_vec(e, y_vec, level));
 	if (x_vec == y_vec) return fail(MGB_EINVAL, "x and y must differ");
-	double *x, *y; TRY(vec_ptr(e, x_vec, level, &x)); TRY(vec_ptr(e, y_vec, level, &y));
-	TRY(k_apply(e, level, x, y));
+	GHOSTS(e, level, x_vec);
+	TRY(k_apply(e, level, x_vec, y_vec));
 	return sync(e);
 }
 extern "C" int mgb_op_residual(mgb_engine *e, int level)
 {
-	NEED(e); TRY(require_ops(e, false));
-	double *x, *b, *r;
-	TRY(vec_ptr(e, MGB_VEC_U, level, &x)); TRY(vec_ptr(e, MGB_VEC_B, level, &b)); TRY(vec_ptr(e, MGB_VEC_R, level, &r));
-	TRY(k_residual(e, level, x, b, r));
+	NEED(e); TRY(require_ops(e, false)); TRY(check_vec(e, MGB_VEC_U, level));
+	GHOSTS(e, level, MGB_VEC_U);
+	TRY(k_residual(e, level, MGB_VEC_U, MGB_VEC_B, MGB_VEC_R));
 	return sync(e);
 }
 extern "C" int mgb_op_residual_norm(mgb_engine *e, int level, double *norm)
 {
-	NEED(e); TRY(require_ops(e, false));
-	double *x, *b; TRY(vec_ptr(e, MGB_VEC_U, level, &x)); TRY(vec_ptr(e, MGB_VEC_B, level, &b));
-	TRY(k_resnorm(e, level, x, b, 0));
-	TRY(read_scalars(e, 0, 1));
-	*norm = e->scal_host[0];
+	NEED(e); TRY(require_ops(e, false)); TRY(check_vec(e, MGB_VEC_U, level));
+	GHOSTS(e, level, MGB_VEC_U);
+	TRY(k_resnorm(e, level, MGB_VEC_U, MGB_VEC_B, 0));
+	TRY(read_scalars(e, 0, 1)); TRY(sync(e));
+	*norm = host_scal(e)[0];
 	return MGB_OK;
 }
 extern "C" int mgb_op_smooth(mgb_engine *e, int level, const mgb_smoother *s, int its, int guess_zero)
 {
-	NEED(e); TRY(require_ops(e, false)); TRY(check_smoother(e, s));
-	if (level < 0 || level >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d out of range", level);
+	NEED(e); TRY(require_ops(e, false)); TRY(check_smoother(e, s)); TRY(check_vec(e, MGB_VEC_U, level));
+	GHOSTS(e, level, MGB_VEC_U);
 	TRY(smooth(e, level, s, its, guess_zero != 0, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));
 	return sync(e);
 }
 extern "C" int mgb_op_restrict(mgb_engine *e, int level, int fused)
 {
 	NEED(e); TRY(require_ops(e, true));
-	if (level < 0 || level + 1 >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d has no coarser level", level);
-	if (fused) { TRY(restrict_fused(e, level, MGB_VEC_B, MGB_VEC_U)); return sync(e); }
-	Level &F = e->lev[level], &C = e->lev[level + 1];
-	double *r, *bc; TRY(vec_ptr(e, MGB_VEC_R, level, &r)); TRY(vec_ptr(e, MGB_VEC_B, level + 1, &bc));
-	dim3 blk(32, 4), g(cdiv(C.pitch, 32), cdiv(C.ni, 4));
-	k_restrict<0><<<g, blk, 0, e->stream>>>(nullptr, nullptr, r, bc, ldev(F), ldev(C), e->R3);
-	LAUNCHED(e); KCHECK();
+	if (level < 0 || level + 1 >= e->L) return fail(MGB_EINVAL, "level %d has no coarser level", level);
+	GHOSTS(e, level, MGB_VEC_U); GHOSTS(e, level, MGB_VEC_B); GHOSTS(e, level, MGB_VEC_R);
+	TRY(restrict_to_coarse(e, level, MGB_VEC_B, MGB_VEC_U, MGB_VEC_R, fused != 0));
 	return sync(e);
 }
 extern "C" int mgb_op_prolong(mgb_engine *e, int level, int multadd)
 {
 	NEED(e); TRY(require_ops(e, true));
-	if (level < 0 || level + 1 >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d has no coarser level", level);
+	if (level < 0 || level + 1 >= e->L) return fail(MGB_EINVAL, "level %d has no coarser level", level);
+	GHOSTS(e, level + 1, MGB_VEC_U);
 	TRY(prolong_add(e, level, MGB_VEC_U, multadd != 0));
 	return sync(e);
 }
 extern "C" int mgb_op_norm2(mgb_engine *e, int which, int level, double *out)
 {
-	NEED(e); double *x; TRY(vec_ptr(e, which, level, &x));
-	TRY(k_reduce(e, level, x, nullptr, 0, 1)); TRY(read_scalars(e, 0, 1));
-	*out = e->scal_host[0]; return MGB_OK;
+	NEED(e); TRY(need_peers(e)); TRY(check_vec(e, which, level));
+	TRY(k_reduce(e, level, which, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); TRY(sync(e));
+	*out = host_scal(e)[0]; return MGB_OK;
 }
 extern "C" int mgb_op_dot(mgb_engine *e, int xw, int yw, int level, double *out)
 {
-	NEED(e); double *x, *y; TRY(vec_ptr(e, xw, level, &x)); TRY(vec_ptr(e, yw, level, &y));
-	TRY(k_reduce(e, level, x, y, 0, 0)); TRY(read_scalars(e, 0, 1));
-	*out = e->scal_host[0]; return MGB_OK;
+	NEED(e); TRY(need_peers(e)); TRY(check_vec(e, xw, level)); TRY(check_vec(e, yw, level));
+	TRY(k_reduce(e, level, xw, yw, 0, 0)); TRY(read_scalars(e, 0, 1)); TRY(sync(e));
+	*out = host_scal(e)[0]; return MGB_OK;
 }
 extern "C" int mgb_op_axpy(mgb_engine *e, int yw, double alpha, int xw, int level)
 {
-	NEED(e); double *x, *y; TRY(vec_ptr(e, xw, level, &x)); TRY(vec_ptr(e, yw, level, &y));
-	TRY(k_vecop<0>(e, level, y, x, alpha)); return sync(e);
+	NEED(e); TRY(check_vec(e, xw, level)); TRY(check_vec(e, yw, level));
+	TRY(k_vecop<0>(e, level, yw, xw, alpha)); return sync(e);
 }
 extern "C" int mgb_op_aypx(mgb_engine *e, int yw, double beta, int xw, int level)
 {
-	NEED(e); double *x, *y; TRY(vec_ptr(e, xw, level, &x)); TRY(vec_ptr(e, yw, level, &y));
-	TRY(k_vecop<1>(e, level, y, x, beta)); return sync(e);
+	NEED(e); TRY(check_vec(e, xw, level)); TRY(check_vec(e, yw, level));
+	TRY(k_vecop<1>(e, level, yw, xw, beta)); return sync(e);
 }
 
 static int csr_spmv_dev(mgb_engine *e, const Csr *c, const double *x, int xn, int xp, double *y, int yn, int yp)
 {
-	k_csr_spmv<<<cdiv(c->m, 256), 256, 0, e->stream>>>(c->rowptr, c->col, c->val, c->m, x, xn, xp, y, yn, yp);
+	k_csr_spmv<<<cdiv(c->m, 256), 256, 0, e->strips[0].stream>>>(c->rowptr, c->col, c->val, c->m, x, xn, xp, y, yn, yp);
 	LAUNCHED(e); KCHECK(); return MGB_OK;
 }
 extern "C" int mgb_csr_spmv_vec(mgb_engine *e, int which, int level, int x_vec, int y_vec)
 {
-	const Csr *c; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
 	const int lx = (which == MGB_MAT_PRO) ? level + 1 : level;
 	const int ly = (which == MGB_MAT_RES) ? level + 1 : level;
 	if (lx == ly && x_vec == y_vec) return fail(MGB_EINVAL, "x and y must differ");
-	double *x, *y; TRY(vec_ptr(e, x_vec, lx, &x)); TRY(vec_ptr(e, y_vec, ly, &y));
-	TRY(csr_spmv_dev(e, c, x, e->lev[lx].nj, e->lev[lx].pitch, y, e->lev[ly].nj, e->lev[ly].pitch));
+	TRY(check_vec(e, x_vec, lx)); TRY(check_vec(e, y_vec, ly));
+	Strip &s = e->strips[0];
+	TRY(csr_spmv_dev(e, c, s.lev[lx].v[x_vec], e->geo[lx].nj, e->geo[lx].pitch, s.lev[ly].v[y_vec], e->geo[ly].nj, e->geo[ly].pitch));
 	return sync(e);
 }
 extern "C" int mgb_csr_spmv(mgb_engine *e, int which, int level, const double *x, double *y)
 {
-	const Csr *c; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
 	if (!x || !y) return fail(MGB_EINVAL, "null argument");
+	cudaStream_t st = e->strips[0].stream;
 	double *dx, *dy;
 	CU(cudaMalloc(&dx, sizeof(double) * (size_t)c->n)); CU(cudaMalloc(&dy, sizeof(double) * (size_t)c->m));
-	CU(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, e->stream));
+	CU(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, st));
 	int r = csr_spmv_dev(e, c, dx, c->n, 0, dy, c->m, 0);   // dense vectors: one "row" of length n
 	if (r == MGB_OK) {
-		cudaError_t ce = cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)c->m, cudaMemcpyDeviceToHost, e->stream);
-		if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+		cudaError_t ce = cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)c->m, cudaMemcpyDeviceToHost, st);
+		if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
 		if (ce != cudaSuccess) r = fail(MGB_ECUDA, "csr spmv copy back: %s", cudaGetErrorString(ce));
 	}
 	cudaFree(dx); cudaFree(dy);
@@ -678,20 +1187,20 @@ extern "C" int mgb_csr_spmv(mgb_engine *e, int which, int level, const double *x
 // the fine residual norm into scal[0].
 static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 {
-	const int Lc = (int)e->lev.size();
+	const int Lc = e->L;
 	const mgb_smoother *s = &p->smoother;
 	TRY(smooth(e, 0, s, p->v0, first, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));                          // :1531-1532
 	for (int l = 1; l < Lc; ++l) {
-		TRY(restrict_fused(e, l - 1, MGB_VEC_B, MGB_VEC_U));                                      // :1534-1535
+		TRY(restrict_to_coarse(e, l - 1, MGB_VEC_B, MGB_VEC_U, MGB_VEC_R, true));                 // :1534-1535
 		TRY(smooth(e, l, s, (l == Lc - 1) ? p->v1 : p->v0, true, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W)); // :1536
 	}
 	for (int l = Lc - 2; l >= 0; --l) {
 		TRY(prolong_add(e, l, MGB_VEC_U, false));                                                 // :1540-1541
 		TRY(smooth(e, l, s, p->v0, false, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));                       // :1542
 	}
-	double *u, *b; TRY(vec_ptr(e, MGB_VEC_U, 0, &u)); TRY(vec_ptr(e, MGB_VEC_B, 0, &b));
-	TRY(k_resnorm(e, 0, u, b, 0));                                                                // :1545-1546
-	CU(cudaMemcpyAsync(e->scal_host, e->scal, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));                                                // :1545-1546
+	Strip &s0 = e->strips[0];
+	CU(cudaMemcpyAsync(s0.scal_host, s0.scal, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
 	return MGB_OK;
 }
 
@@ -700,29 +1209,43 @@ static void drop_graphs(mgb_engine *e)
 	for (int g = 0; g < 2; ++g) if (e->gexec[g]) { cudaGraphExecDestroy(e->gexec[g]); e->gexec[g] = nullptr; }
 }
 
+struct PtrState { double *v[MGB_MAXL][MGB_NVEC]; int phys[MGB_MAXL][MGB_NVEC]; };
+static void save_state(mgb_engine *e, std::vector<PtrState> &st)
+{
+	st.resize(e->strips.size());
+	for (size_t i = 0; i < e->strips.size(); ++i)
+		for (int l = 0; l < e->L; ++l)
+			for (int k = 0; k < MGB_NVEC; ++k) { st[i].v[l][k] = e->strips[i].lev[l].v[k]; st[i].phys[l][k] = e->strips[i].lev[l].phys[k]; }
+}
+static void load_state(mgb_engine *e, const std::vector<PtrState> &st)
+{
+	for (size_t i = 0; i < e->strips.size(); ++i)
+		for (int l = 0; l < e->L; ++l)
+			for (int k = 0; k < MGB_NVEC; ++k) { e->strips[i].lev[l].v[k] = st[i].v[l][k]; e->strips[i].lev[l].phys[k] = st[i].phys[l][k]; }
+}
+
 extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter, double *seconds)
 {
 	NEED(e);
 	if (!p || !rnorm || !num_iter) return fail(MGB_EINVAL, "null argument");
 	TRY(require_ops(e, true)); TRY(check_smoother(e, &p->smoother));
 	if (p->v0 < 0 || p->v1 < 0 || p->max_iter < 0) return fail(MGB_EINVAL, "negative sweep or iteration count");
-	double *u, *b; TRY(vec_ptr(e, MGB_VEC_U, 0, &u)); TRY(vec_ptr(e, MGB_VEC_B, 0, &b));
+	Strip &s0 = e->strips[0];
 	// bnorm = ||b0|| ; u0 = 0 ; rnorm[0] = ||A0 u0 - b0||                                      (:1512-1520)
-	TRY(k_reduce(e, 0, b, nullptr, 1, 1));
+	GHOSTS(e, 0, MGB_VEC_B);
+	TRY(k_reduce(e, 0, MGB_VEC_B, -1, 1, 1));
 	TRY(vec_zero(e, MGB_VEC_U, 0));
-	TRY(k_resnorm(e, 0, u, b, 0));
-	TRY(read_scalars(e, 0, 2));
-	const double bnorm = e->scal_host[1];
-	double rn = e->scal_host[0];
+	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));
+	TRY(read_scalars(e, 0, 2)); TRY(sync(e));
+	const double bnorm = host_scal(e)[1];
+	double rn = host_scal(e)[0];
 	rnorm[0] = rn;
 	int iter = 0;
 	drop_graphs(e);
 	long long launches_per_graph[2] = {0, 0};
-	double *state_u[2][64], *state_w[2][64];
-	const int Lc = (int)e->lev.size();
-	if (Lc > 64) return fail(MGB_EINVAL, "too many levels");
+	std::vector<PtrState> state_after[2];
 	const auto t0 = std::chrono::steady_clock::now();
-	CU(cudaEventRecord(e->ev0, e->stream));
+	CU(cudaEventRecord(s0.ev0, s0.stream));
 	int gphase = 0;
 	while (iter < p->max_iter && 100000000.0 * bnorm > rn && rn > p->rtol * bnorm) {              // :1530
 		if (!p->use_graph || iter == 0) {
@@ -732,34 +1255,35 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 				// capture this phase: the pointer state before/after is a pure function of the phase
 				cudaGraph_t g;
 				const long long l0 = e->launches;
-				CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+				CU(cudaStreamBeginCapture(s0.stream, cudaStreamCaptureModeThreadLocal));
 				int r = vcycle_body(e, p, false);
-				cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+				cudaError_t ce = cudaStreamEndCapture(s0.stream, &g);
 				if (r != MGB_OK) return r;
 				if (ce != cudaSuccess) return fail(MGB_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
 				CU(cudaGraphInstantiate(&e->gexec[gphase], g, 0));
 				cudaGraphDestroy(g);
 				launches_per_graph[gphase] = e->launches - l0;
 				e->launches = l0;
-				for (int l = 0; l < Lc; ++l) { state_u[gphase][l] = e->lev[l].v[MGB_VEC_U]; state_w[gphase][l] = e->lev[l].v[MGB_VEC_W]; }
+				save_state(e, state_after[gphase]);
 			} else {
-				for (int l = 0; l < Lc; ++l) { e->lev[l].v[MGB_VEC_U] = state_u[gphase][l]; e->lev[l].v[MGB_VEC_W] = state_w[gphase][l]; }
+				load_state(e, state_after[gphase]);
 			}
-			CU(cudaGraphLaunch(e->gexec[gphase], e->stream));
+			CU(cudaGraphLaunch(e->gexec[gphase], s0.stream));
 			e->launches += launches_per_graph[gphase];
 			gphase ^= 1;
 		}
-		CU(cudaStreamSynchronize(e->stream));
-		rn = e->scal_host[0];
+		CU(cudaStreamSynchronize(s0.stream));
+		rn = s0.scal_host[0];
 		iter = iter + 1;
 		rnorm[iter] = rn;
 	}
-	CU(cudaEventRecord(e->ev1, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
+	CU(cudaEventRecord(s0.ev1, s0.stream));
+	CU(cudaStreamSynchronize(s0.stream));
 	const auto t1 = std::chrono::steady_clock::now();
 	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
-	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_solve_ms = ms; }
+	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, s0.ev0, s0.ev1)); e->last_solve_ms = ms; }
 	drop_graphs(e);
+	TRY(check_status(e));
 	const double r0 = rnorm[0];
 	for (int i = 0; i <= iter; ++i) rnorm[i] = rnorm[i] / r0;                                     // :1554-1557
 	*num_iter = iter;
@@ -770,18 +1294,20 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 // PCApply_MG (multiplicative V, one cycle, x = 0 on entry) on level l with right-hand side bv and iterate xv.
 static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, int xv)
 {
-	const int Lc = (int)e->lev.size();
+	const int Lc = e->L;
 	if (l == Lc - 1) {
 		if (p->coarse == MGB_COARSE_RICHARDSON)
 			return smooth(e, l, &p->coarse_smoother, p->coarse_its, true, bv, xv, MGB_VEC_W);
-		Level &L = e->lev[l];
-		double *b, *x; TRY(vec_ptr(e, bv, l, &b)); TRY(vec_ptr(e, xv, l, &x));
-		TRY(bandlu_solve(L.lu, b, x, L.ni, L.nj, L.pitch, e->stream));
-		LAUNCHED(e);
+		for (auto &s : e->strips) {
+			if (!computes(s, l)) continue;
+			SLevel &S = s.lev[l];
+			if (bandlu_solve(S.lu, S.v[bv], S.v[xv], S.ni, e->geo[l].nj, e->geo[l].pitch, s.stream)) return fail(MGB_ECUDA, "coarse LU solve launch failed");
+			LAUNCHED(e);
+		}
 		return MGB_OK;
 	}
 	TRY(smooth(e, l, &p->level_smoother, p->level_its, true, bv, xv, MGB_VEC_W));     // pre-smooth from x = 0
-	TRY(restrict_fused(e, l, bv, xv));                                                // b_c = R (b - A x)
+	TRY(restrict_to_coarse(e, l, bv, xv, MGB_VEC_R, true));                           // b_c = R (b - A x)
 	TRY(pcmg_cycle(e, p, l + 1, MGB_VEC_B, MGB_VEC_U));                               // x_c = 0 ; recurse
 	TRY(prolong_add(e, l, xv, true));                                                 // x = x + P x_c (MatMultAdd)
 	TRY(smooth(e, l, &p->level_smoother, p->level_its, false, bv, xv, MGB_VEC_W));    // post-smooth
@@ -803,7 +1329,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 	NEED(e);
 	if (!p || !rnorm || !num_iter) return fail(MGB_EINVAL, "null argument");
 	TRY(require_ops(e, true));
-	const int Lc = (int)e->lev.size();
+	const int Lc = e->L;
 	if (Lc < 2) return fail(MGB_EINVAL, "cycle 8 needs at least two levels");
 	TRY(check_smoother(e, &p->level_smoother));
 	if (p->coarse == MGB_COARSE_RICHARDSON) {
@@ -812,54 +1338,61 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 		    p->coarse_smoother.omega != p->level_smoother.omega)
 			return fail(MGB_EINVAL, "different SOR omegas on levels and coarse grid are not supported");
 	} else if (p->coarse == MGB_COARSE_LU) {
-		Level &C = e->lev[Lc - 1];
-		TRY(bandlu_factor(C.lu, C.coef_host.data(), C.ni, C.nj, g_err, sizeof g_err));
+		if (e->geo[Lc - 1].dist) return fail(MGB_EINVAL, "coarse LU needs the coarsest level agglomerated on rank 0");
+		for (auto &s : e->strips) {
+			if (!computes(s, Lc - 1)) continue;
+			SLevel &C = s.lev[Lc - 1];
+			if (bandlu_factor(C.lu, e->geo[Lc - 1].coef_host.data(), C.ni, e->geo[Lc - 1].nj, g_err, sizeof g_err)) return MGB_EINVAL;
+		}
 	} else return fail(MGB_EINVAL, "unknown coarse solver %d", p->coarse);
 	if (p->outer != MGB_KSP_CG && p->outer != MGB_KSP_RICHARDSON) return fail(MGB_EINVAL, "unknown outer KSP %d", p->outer);
 
-	double *X, *B, *R, *Z, *P, *Q;
-	TRY(vec_ptr(e, MGB_VEC_U, 0, &X)); TRY(vec_ptr(e, MGB_VEC_B, 0, &B)); TRY(vec_ptr(e, MGB_VEC_R, 0, &R));
-	TRY(vec_ptr(e, MGB_VEC_Z, 0, &Z)); TRY(vec_ptr(e, MGB_VEC_P, 0, &P)); TRY(vec_ptr(e, MGB_VEC_Q, 0, &Q));
-	CU(cudaStreamSynchronize(e->stream));
+	const int X = MGB_VEC_U, B = MGB_VEC_B, R = MGB_VEC_R, Z = MGB_VEC_Z, Pv = MGB_VEC_P, Q = MGB_VEC_Q;
+	Strip &s0 = e->strips[0];
+	TRY(sync_all(e));
 	const auto t0 = std::chrono::steady_clock::now();
-	CU(cudaEventRecord(e->ev0, e->stream));
+	CU(cudaEventRecord(s0.ev0, s0.stream));
 	int reason = 0, its = 0, nlog = 0;
 	double rnorm0 = 0.0, ttol = 0.0, dp = 0.0;
 	auto logr = [&](double v) { if (nlog < p->max_iter) rnorm[nlog++] = v; };   // KSPSetResidualHistory(na = numIter)
 	for (int i = 0; i <= p->max_iter; ++i) rnorm[i] = NAN;
+	double *hs = host_scal(e);
+	// z = B r : one multigrid cycle on (r, z); the ghost rows of r are refreshed first (the restriction reads them)
+	auto precond = [&]() -> int { TRY(halo(e, 0, R, 2)); return pcmg_cycle(e, p, 0, R, Z); };
 
-	TRY(vec_zero(e, MGB_VEC_U, 0));                          // KSPSolve: zero initial guess
+	TRY(vec_zero(e, X, 0));                                  // KSPSolve: zero initial guess
 	TRY(k_vecop<2>(e, 0, R, B, 0.0));                        // r = b
 	if (p->outer == MGB_KSP_CG) {
 		// KSPSolve_CG, KSP_NORM_UNPRECONDITIONED (ref: src/solver.c:1922)
 		double beta = 0.0, betaold = 1.0, dpi = 0.0, dpiold;
-		TRY(k_reduce(e, 0, R, nullptr, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = e->scal_host[0];
+		TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
 		logr(dp);
 		reason = ksp_converged(p, 0, dp, &rnorm0, &ttol);
 		if (!reason) {
-			TRY(pcmg_cycle(e, p, 0, MGB_VEC_R, MGB_VEC_Z)); TRY(vec_ptr(e, MGB_VEC_Z, 0, &Z));     // z = B r
-			TRY(k_reduce(e, 0, Z, R, 0, 0)); TRY(read_scalars(e, 0, 1)); beta = e->scal_host[0];   // beta = z'r
+			TRY(precond());                                                                        // z = B r
+			TRY(k_reduce(e, 0, Z, R, 0, 0)); TRY(read_scalars(e, 0, 1)); beta = hs[0];             // beta = z'r
 			int i = 0;
 			do {
 				its = i + 1;
 				if (beta == 0.0) { reason = 3; break; }
 				else if (i > 0 && beta * betaold < 0.0) { reason = -8; break; }                    // KSP_DIVERGED_INDEFINITE_PC
-				if (i == 0) { TRY(k_vecop<2>(e, 0, P, Z, 0.0)); }                                  // p = z
-				else { TRY(k_vecop<1>(e, 0, P, Z, beta / betaold)); }                              // p = z + b p
+				if (i == 0) { TRY(k_vecop<2>(e, 0, Pv, Z, 0.0)); }                                 // p = z
+				else { TRY(k_vecop<1>(e, 0, Pv, Z, beta / betaold)); }                             // p = z + b p
 				dpiold = dpi;
-				TRY(k_apply(e, 0, P, Q));                                                          // w = A p
-				TRY(k_reduce(e, 0, P, Q, 0, 0)); TRY(read_scalars(e, 0, 1)); dpi = e->scal_host[0];
+				TRY(halo(e, 0, Pv, 2));
+				TRY(k_apply(e, 0, Pv, Q));                                                         // w = A p
+				TRY(k_reduce(e, 0, Pv, Q, 0, 0)); TRY(read_scalars(e, 0, 1)); dpi = hs[0];
 				betaold = beta;
 				if (dpi == 0.0 || (i > 0 && dpi * dpiold <= 0.0)) { reason = -10; break; }         // KSP_DIVERGED_INDEFINITE_MAT
 				const double a = beta / dpi;
-				TRY(k_vecop<0>(e, 0, X, P, a));                                                    // x = x + a p
+				TRY(k_vecop<0>(e, 0, X, Pv, a));                                                   // x = x + a p
 				TRY(k_vecop<0>(e, 0, R, Q, -a));                                                   // r = r - a w
-				TRY(k_reduce(e, 0, R, nullptr, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = e->scal_host[0];
+				TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
 				logr(dp);
 				reason = ksp_converged(p, i + 1, dp, &rnorm0, &ttol);
 				if (reason) break;
-				TRY(pcmg_cycle(e, p, 0, MGB_VEC_R, MGB_VEC_Z)); TRY(vec_ptr(e, MGB_VEC_Z, 0, &Z));
-				TRY(k_reduce(e, 0, Z, R, 0, 0)); TRY(read_scalars(e, 0, 1)); beta = e->scal_host[0];
+				TRY(precond());
+				TRY(k_reduce(e, 0, Z, R, 0, 0)); TRY(read_scalars(e, 0, 1)); beta = hs[0];
 				i++;
 			} while (i < p->max_iter);
 			if (i >= p->max_iter && !reason) reason = -3;                                          // KSP_DIVERGED_ITS
@@ -867,26 +1400,28 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 	} else {
 		// KSPSolve_Richardson, general path (residual norm logged every iteration), scale 1
 		for (int i = 0; i < p->max_iter; ++i) {
-			TRY(k_reduce(e, 0, R, nullptr, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = e->scal_host[0];
+			TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
 			logr(dp);
 			reason = ksp_converged(p, i, dp, &rnorm0, &ttol);
 			if (reason) break;
-			TRY(pcmg_cycle(e, p, 0, MGB_VEC_R, MGB_VEC_Z)); TRY(vec_ptr(e, MGB_VEC_Z, 0, &Z));     // z = B r
+			TRY(precond());                                                                        // z = B r
 			TRY(k_vecop<0>(e, 0, X, Z, 1.0));                                                      // x = x + scale z
 			its++;
+			TRY(halo(e, 0, X, 2));
 			TRY(k_residual(e, 0, X, B, R));                                                        // r = b - A x
 		}
 		if (!reason) {
-			TRY(k_reduce(e, 0, R, nullptr, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = e->scal_host[0];
+			TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
 			logr(dp);
 			if (its >= p->max_iter) { reason = ksp_converged(p, its, dp, &rnorm0, &ttol); if (!reason) reason = -3; }
 		}
 	}
-	CU(cudaEventRecord(e->ev1, e->stream));
-	CU(cudaStreamSynchronize(e->stream));
+	CU(cudaEventRecord(s0.ev1, s0.stream));
+	TRY(sync_all(e));
 	const auto t1 = std::chrono::steady_clock::now();
 	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
-	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1)); e->last_solve_ms = ms; }
+	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, s0.ev0, s0.ev1)); e->last_solve_ms = ms; }
+	TRY(check_status(e));
 	// ref: src/solver.c:1971-1976 -- numIter = KSPGetIterationNumber ; rnorm[i] /= rnorm[0]
 	const double r0 = rnorm[0];
 	for (int i = 0; i < its + 1 && i <= p->max_iter; ++i) rnorm[i] = rnorm[i] / r0;
@@ -899,40 +1434,40 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *ms_per_launch)
 {
 	NEED(e); TRY(require_ops(e, true));
-	if (level < 0 || level >= (int)e->lev.size()) return fail(MGB_EINVAL, "level %d out of range", level);
+	if (level < 0 || level >= e->L) return fail(MGB_EINVAL, "level %d out of range", level);
 	if (reps < 1 || !ms_per_launch) return fail(MGB_EINVAL, "bad reps / null output");
-	double *u, *b, *r, *w;
-	TRY(vec_ptr(e, MGB_VEC_U, level, &u)); TRY(vec_ptr(e, MGB_VEC_B, level, &b));
-	TRY(vec_ptr(e, MGB_VEC_R, level, &r)); TRY(vec_ptr(e, MGB_VEC_W, level, &w));
+	if (e->strips.size() != 1) return fail(MGB_EINVAL, "mgb_time_op times one strip per process");
 	mgb_smoother jac = {MGB_SMOOTH_JACOBI, 0.8, 1.0, 0, 1};
-	const bool has_coarse = level + 1 < (int)e->lev.size();
+	const bool has_coarse = level + 1 < e->L;
 	if ((op == 4 || op == 5) && !has_coarse) return fail(MGB_EINVAL, "level %d has no coarser level", level);
 	if (op == 7 && !e->csr_built) return fail(MGB_ESTATE, "mgb_assemble_csr was not called");
 	TRY(set_sor_omega(e, 1.0));
+	Strip &s = e->strips[0];
+	const int U = MGB_VEC_U, B = MGB_VEC_B, R = MGB_VEC_R;
 	for (int pass = 0; pass < 2; ++pass) {
 		const int n = pass == 0 ? 2 : reps;                   // pass 0: warm-up
-		if (pass == 1) CU(cudaEventRecord(e->ev0, e->stream));
+		if (pass == 1) CU(cudaEventRecord(s.ev0, s.stream));
 		for (int k = 0; k < n; ++k) {
 			switch (op) {
-			case 0: TRY(k_apply(e, level, u, r)); break;
-			case 1: TRY(k_residual(e, level, u, b, r)); break;
-			case 2: TRY(smooth(e, level, &jac, 1, false, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W)); break;
-			case 3: TRY(k_rb(e, level, u, b, 0, 1.0, 0)); TRY(k_rb(e, level, u, b, 1, 1.0, 0)); break;
-			case 4: TRY(restrict_fused(e, level, MGB_VEC_B, MGB_VEC_U)); break;
-			case 5: TRY(prolong_add(e, level, MGB_VEC_U, false)); break;
-			case 6: TRY(k_resnorm(e, level, u, b, 0)); break;
-			case 7: TRY(csr_spmv_dev(e, &e->lev[level].A, u, e->lev[level].nj, e->lev[level].pitch, r, e->lev[level].nj, e->lev[level].pitch)); break;
-			case 8: TRY(k_reduce(e, level, u, nullptr, 0, 1)); break;
-			case 9: TRY(k_reduce(e, level, u, b, 0, 0)); break;
-			case 10: TRY(k_vecop<0>(e, level, r, u, 0.5)); break;
+			case 0: TRY(k_apply(e, level, U, R)); break;
+			case 1: TRY(k_residual(e, level, U, B, R)); break;
+			case 2: TRY(smooth(e, level, &jac, 1, false, B, U, MGB_VEC_W)); break;
+			case 3: TRY(k_rb(e, level, U, B, 0, 1.0, 0)); TRY(k_rb(e, level, U, B, 1, 1.0, 0)); break;
+			case 4: TRY(restrict_to_coarse(e, level, B, U, R, true)); break;
+			case 5: TRY(prolong_add(e, level, U, false)); break;
+			case 6: TRY(k_resnorm(e, level, U, B, 0)); break;
+			case 7: { SLevel &S = s.lev[level]; TRY(csr_spmv_dev(e, &S.A, S.v[U], e->geo[level].nj, e->geo[level].pitch, S.v[R], e->geo[level].nj, e->geo[level].pitch)); } break;
+			case 8: TRY(k_reduce(e, level, U, -1, 0, 1)); break;
+			case 9: TRY(k_reduce(e, level, U, B, 0, 0)); break;
+			case 10: TRY(k_vecop<0>(e, level, R, U, 0.5)); break;
 			default: return fail(MGB_EINVAL, "unknown op %d", op);
 			}
 		}
-		if (pass == 1) CU(cudaEventRecord(e->ev1, e->stream));
-		CU(cudaStreamSynchronize(e->stream));
+		if (pass == 1) CU(cudaEventRecord(s.ev1, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
 	}
 	float ms = 0.f;
-	CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+	CU(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
 	*ms_per_launch = (double)ms / reps;
-	return MGB_OK;
+	return check_status(e);
 }

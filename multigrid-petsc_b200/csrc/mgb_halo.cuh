@@ -1,0 +1,110 @@
+// mgb_halo.cuh -- strip-to-strip data movement over NVLink peer memory: ghost-row exchange, gather of the first
+// agglomerated level onto rank 0, broadcast of its correction, all-reduce of norm/dot partials.
+//
+// Replaces what PETSc's MPIAIJ VecScatter (ghost values of every MatMult), MPI_Allreduce (VecNorm/VecDot) and
+// the hand-written MPI_Send/MPI_Recv gather (ref: src/solver.c:1273-1299) do for the reference.  There is no
+// NCCL call on this path: one generic kernel stores rows straight into the peer's HBM (addresses obtained with
+// cudaIpcOpenMemHandle, or plain device pointers when several strips live in one process) and then raises a
+// flag in the peer's memory; the receiving side spins on its own flag word.
+//
+// Protocol.  Every transfer site is a CHANNEL c with a device-resident version counter ver[c] that all ranks
+// advance in lock step (every rank launches the kernel for every use of a channel, even with nothing to send).
+//   push:  newv = ver[c] + 1; all blocks copy their share; the last block to finish (atomic ticket) issues
+//          __threadfence_system(), stores newv into flag[c][my_rank] of every destination (st.release.sys)
+//          and sets ver[c] = newv.
+//   wait:  v = ver[c]; spin (ld.acquire.sys) until flag[c][src] >= v for every expected source.
+// In a multi-process run (one strip per process, one GPU each) push and wait are ONE launch: the last block
+// signals and then waits, so a rank can never run more than one exchange ahead of its neighbours (this is what
+// makes overwriting the neighbour's ghost rows safe, see DESIGN.md "Halo protocol").  When several strips are
+// emulated on one GPU (tests) the engine launches all pushes first and the waits afterwards, so that no kernel
+// ever waits for a kernel queued behind it.  Spins are bounded (~4 s): on timeout status[0] is set and the
+// host reports MGB_ECUDA instead of hanging the GPU.
+#pragma once
+#include "mgb_common.cuh"
+
+#define MGB_MAX_RANKS 8
+#define MGB_XFER_THREADS 256
+
+struct XferArgs {
+	int ndst;                                       // destinations of this launch (0..MGB_MAX_RANKS)
+	const double *src[MGB_MAX_RANKS];
+	double *dst[MGB_MAX_RANKS];
+	unsigned long long cnt2[MGB_MAX_RANKS];         // double2 elements to copy per destination
+	unsigned long long *peer_flag[MGB_MAX_RANKS];   // flag word in the destination's memory (its flag[c][my_rank])
+	int nwait;
+	const unsigned long long *wait_flag[MGB_MAX_RANKS]; // my own flag words flag[c][src_rank]
+	unsigned long long *ver;                        // my version counter of the channel
+	unsigned int *ticket;                           // my block ticket counter of the channel (zero between launches)
+	int *status;                                    // status[0] != 0 after a timeout
+	int do_push, do_wait;
+	long long spin_limit;                           // clock64 ticks
+	unsigned long long parity_stride;               // doubles added to every dst when the new version is odd (all-reduce slots)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(MGB_XFER_THREADS)
+k_xfer(XferArgs a)
+{
+	__shared__ int is_last;
+	if (a.do_push) {
+		// safe to read: ver is only advanced by the last block, after every block has taken its ticket
+		const unsigned long long par = (a.parity_stride && ((*a.ver + 1ull) & 1ull)) ? a.parity_stride : 0ull;
+		for (int d = 0; d < a.ndst; ++d) {
+			const double2 *s = reinterpret_cast<const double2 *>(a.src[d]);
+			double2 *t = reinterpret_cast<double2 *>(a.dst[d] + par);
+			for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.cnt2[d];
+			     k += (unsigned long long)gridDim.x * blockDim.x)
+				t[k] = s[k];
+		}
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const unsigned int t = atomicAdd(a.ticket, 1u);
+			is_last = (t == gridDim.x - 1);
+		}
+		__syncthreads();
+		if (!is_last) return;
+		if (threadIdx.x == 0) {
+			*a.ticket = 0u;
+			const unsigned long long newv = *a.ver + 1ull;
+			__threadfence_system();
+			for (int d = 0; d < a.ndst; ++d) st_release_sys(a.peer_flag[d], newv);
+			*a.ver = newv;
+		}
+	} else if (blockIdx.x != 0) return;
+	if (a.do_wait && threadIdx.x == 0) {
+		const unsigned long long v = *(volatile unsigned long long *)a.ver;
+		const long long t0 = clock64();
+		for (int w = 0; w < a.nwait; ++w) {
+			while (ld_acquire_sys(a.wait_flag[w]) < v) {
+				if (clock64() - t0 > a.spin_limit) { atomicExch(a.status, 1); break; }
+				__nanosleep(40);
+			}
+		}
+		__threadfence_system();
+	}
+}
+
+// out[out_slot + k] = f(sum over ranks of slot[r][k]) in rank order (identical on every rank): the all-reduce tail.
+// slots: two parity sets of MGB_MAX_RANKS x 4 doubles (the set of the version just completed is read, so a fast
+// rank's next all-reduce cannot overwrite values a slow rank has not summed yet); take_sqrt applies to value 0.
+__global__ void k_reduce_ranks(const double *__restrict__ slots, unsigned long long parity_stride,
+                               const unsigned long long *__restrict__ ver, int nranks, int nvals,
+                               double *__restrict__ out, int out_slot, int take_sqrt)
+{
+	if (threadIdx.x >= nvals) return;
+	const double *sl = slots + ((*ver & 1ull) ? parity_stride : 0ull);
+	double s = 0.0;
+	for (int r = 0; r < nranks; ++r) s += sl[r * 4 + threadIdx.x];
+	out[out_slot + threadIdx.x] = (take_sqrt && threadIdx.x == 0) ? sqrt(s) : s;
+}

@@ -1,6 +1,6 @@
 // mgb_stencil.cuh -- matrix-free 5-point kernels: apply, residual, residual norm, weighted-Jacobi sweep,
 // red-black SOR half sweep.  One thread owns two adjacent columns (16-byte loads/stores) and streams down
-// RY grid rows keeping a three-row register window, so every x value is fetched from L2/HBM once per block
+// ry grid rows keeping a three-row register window, so every x value is fetched from L2/HBM once per block
 // (+2 halo rows per RY) and the west/east neighbours come from two extra (L1-resident) scalar loads.
 //
 // Algorithmic HBM bytes per unknown: apply 16, residual 24, residual norm 16, Jacobi sweep 24,
@@ -15,14 +15,14 @@ enum { ST_APPLY = 0, ST_RESID = 1, ST_RESNORM = 2, ST_JACOBI = 3 };
 
 // x: input vector, b: right-hand side (unused for ST_APPLY), y: output (unused for ST_RESNORM)
 // partial: one double per block (ST_RESNORM)
-template <int MODE, int RY>
+template <int MODE>
 __global__ void __launch_bounds__(MGB_SB_THREADS)
 k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
-          LevelDev L, double scale, double *__restrict__ partial)
+          LevelDev L, double scale, double *__restrict__ partial, int ry)
 {
 	const int j0 = (blockIdx.x * MGB_SB_THREADS + threadIdx.x) * 2;
-	const int ibeg = blockIdx.y * RY;
-	const int iend = min(ibeg + RY, L.ni);
+	const int ibeg = blockIdx.y * ry;
+	const int iend = min(ibeg + ry, L.ni);
 	double acc = 0.0;
 	if (j0 < L.pitch) {
 		const size_t P = (size_t)L.pitch;
@@ -43,8 +43,11 @@ k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__
 				aS = cf[0]; aW = cf[1]; aC = cf[2]; aE = cf[3]; aN = cf[4]; dinv = cf[5];
 				cf += MGB_COEF_STRIDE;
 			}
-			const double t0 = stencil5(aS, aW, aC, aE, aN, xm.x, xw, xc.x, xc.y, xn.x);
-			const double t1 = stencil5(aS, aW, aC, aE, aN, xm.y, xc.x, xc.y, xe, xn.y);
+			// column j0 is even: point (i, j0) is red when the global row is even, (i, j0+1) has the other colour
+			const int rowpar = (L.i0 + i) & 1;
+			const int o0 = L.rb ? 1 + rowpar : 0, o1 = L.rb ? 2 - rowpar : 0;
+			const double t0 = stencil5_ord(o0, aS, aW, aC, aE, aN, xm.x, xw, xc.x, xc.y, xn.x);
+			const double t1 = stencil5_ord(o1, aS, aW, aC, aE, aN, xm.y, xc.x, xc.y, xe, xn.y);
 			double2 out;
 			if (MODE == ST_APPLY) {
 				out.x = t0; out.y = t1;
@@ -97,13 +100,13 @@ k_jacobi_first(const double *__restrict__ b, double *__restrict__ x, LevelDev L,
 // including the diagonal and adds it back:  x = (1-omega) x + (sum + diag*x) * idiag.
 // The other colour's values are never written by this launch, so the in-place update is race free; the
 // thread writes back its whole 16-byte pair (the partner value unchanged).
-template <int VARIANT, int RY>
+template <int VARIANT>
 __global__ void __launch_bounds__(MGB_SB_THREADS)
-k_rb_half(double *__restrict__ x, const double *__restrict__ b, LevelDev L, int colour, double omega)
+k_rb_half(double *__restrict__ x, const double *__restrict__ b, LevelDev L, int colour, double omega, int ry)
 {
 	const int j0 = (blockIdx.x * MGB_SB_THREADS + threadIdx.x) * 2;
-	const int ibeg = blockIdx.y * RY;
-	const int iend = min(ibeg + RY, L.ni);
+	const int ibeg = blockIdx.y * ry;
+	const int iend = min(ibeg + ry, L.ni);
 	if (j0 >= L.pitch) return;
 	const size_t P = (size_t)L.pitch;
 	double *xp = x + (size_t)ibeg * P + j0;

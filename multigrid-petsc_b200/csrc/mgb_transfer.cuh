@@ -22,7 +22,7 @@ k_restrict(const double *__restrict__ uf, const double *__restrict__ bf, const d
 	double out = 0.0;
 	if (J < C.nj) {
 		const size_t P = (size_t)F.pitch;
-		double sum = 0.0;
+		double r[9];
 #pragma unroll
 		for (int a = 0; a < 3; ++a) {
 			const int i = 2 * I + a;
@@ -34,16 +34,32 @@ k_restrict(const double *__restrict__ uf, const double *__restrict__ bf, const d
 #pragma unroll
 			for (int b = 0; b < 3; ++b) {
 				const size_t o = (size_t)i * P + (2 * J + b);
-				double r;
 				if (FUSED) {
-					const double t = stencil5(aS, aW, aC, aE, aN, uf[o - P], uf[o - 1], uf[o], uf[o + 1], uf[o + P]);
-					r = sub(bf[o], t);
+					// F.i0 is even (strips start on even fine rows), so the colour of fine (2I+a, 2J+b) is (a+b) & 1
+					const int ord = F.rb ? 1 + ((a + b) & 1) : 0;
+					const double t = stencil5_ord(ord, aS, aW, aC, aE, aN, uf[o - P], uf[o - 1], uf[o], uf[o + 1], uf[o + P]);
+					r[a * 3 + b] = sub(bf[o], t);
 				} else {
-					r = rf[o];
+					r[a * 3 + b] = rf[o];
 				}
-				const double term = mul(R.w[a * 3 + b], r);
-				sum = (a == 0 && b == 0) ? term : add(sum, term);
 			}
+		}
+		double sum;
+		if (!F.rb) {
+			sum = mul(R.w[0], r[0]);
+#pragma unroll
+			for (int k = 1; k < 9; ++k) sum = add(sum, mul(R.w[k], r[k]));
+		} else {
+			// red-first numbering of the fine grid: the five red fine points, then the four black ones
+			sum = mul(R.w[0], r[0]);
+			sum = add(sum, mul(R.w[2], r[2]));
+			sum = add(sum, mul(R.w[4], r[4]));
+			sum = add(sum, mul(R.w[6], r[6]));
+			sum = add(sum, mul(R.w[8], r[8]));
+			sum = add(sum, mul(R.w[1], r[1]));
+			sum = add(sum, mul(R.w[3], r[3]));
+			sum = add(sum, mul(R.w[5], r[5]));
+			sum = add(sum, mul(R.w[7], r[7]));
 		}
 		out = sum;
 	}
@@ -67,35 +83,52 @@ k_prolong_add(double *__restrict__ uf, const double *__restrict__ uc, LevelDev F
 	double2 u = ld2(uf + o);
 	const int J0 = j0 >> 1, Jm = J0 - 1;
 	const size_t PC = (size_t)C.pitch;
-	double e0, e1;       // corrections (MULTADD 0) or running sums (MULTADD 1) for columns j0, j0+1
+	// up to four terms for column j0 (t0..t3) and two for column j0+1 (s0, s1), in the order of the entries of the
+	// row of pro[l]: ascending coarse number -- natural, or red-first (-map 3) where a red coarse point precedes a black one
+	double t0, t1, t2 = 0.0, t3 = 0.0, s0, s1 = 0.0;
+	int nt, ns;
 	if (i & 1) {
 		// a = 1: single coarse row I = (i-1)/2
-		const double *c = uc + (size_t)((i - 1) >> 1) * PC;
-		const double cm = c[Jm], c0 = c[J0];
-		if (MULTADD) {
-			e0 = add(add(u.x, mul(Pw.w[3 + 2], cm)), mul(Pw.w[3 + 0], c0));
-			e1 = add(u.y, mul(Pw.w[3 + 1], c0));
-		} else {
-			e0 = add(mul(Pw.w[3 + 2], cm), mul(Pw.w[3 + 0], c0));
-			e1 = mul(Pw.w[3 + 1], c0);
-		}
+		const int I = (i - 1) >> 1;
+		const double *c = uc + (size_t)I * PC;
+		const double cm = mul(Pw.w[3 + 2], c[Jm]), c0 = mul(Pw.w[3 + 0], c[J0]);
+		const bool swap = F.rb && (((C.i0 + I + Jm) & 1) != 0);      // (I,Jm) black: the red (I,J0) comes first
+		t0 = swap ? c0 : cm; t1 = swap ? cm : c0; nt = 2;
+		s0 = mul(Pw.w[3 + 1], c[J0]); ns = 1;
 	} else {
-		// coarse rows I = i/2 - 1 (a = 2) then I = i/2 (a = 0)
-		const double *cA = uc + (size_t)((i >> 1) - 1) * PC;   // row -1 is the zero ghost row
+		// coarse rows IA = i/2 - 1 (a = 2) then IB = i/2 (a = 0)
+		const int IA = (i >> 1) - 1;
+		const double *cA = uc + (size_t)IA * PC;     // row -1 is the ghost row above the strip
 		const double *cB = cA + PC;
-		const double am = cA[Jm], a0 = cA[J0], bm = cB[Jm], b0 = cB[J0];
-		if (MULTADD) {
-			e0 = add(add(add(add(u.x, mul(Pw.w[6 + 2], am)), mul(Pw.w[6 + 0], a0)), mul(Pw.w[0 + 2], bm)), mul(Pw.w[0 + 0], b0));
-			e1 = add(add(u.y, mul(Pw.w[6 + 1], a0)), mul(Pw.w[0 + 1], b0));
-		} else {
-			e0 = add(add(add(mul(Pw.w[6 + 2], am), mul(Pw.w[6 + 0], a0)), mul(Pw.w[0 + 2], bm)), mul(Pw.w[0 + 0], b0));
-			e1 = add(mul(Pw.w[6 + 1], a0), mul(Pw.w[0 + 1], b0));
+		const double am = mul(Pw.w[6 + 2], cA[Jm]), a0 = mul(Pw.w[6 + 0], cA[J0]);
+		const double bm = mul(Pw.w[0 + 2], cB[Jm]), b0 = mul(Pw.w[0 + 0], cB[J0]);
+		const double sa = mul(Pw.w[6 + 1], cA[J0]), sb = mul(Pw.w[0 + 1], cB[J0]);
+		nt = 4; ns = 2;
+		if (!F.rb) { t0 = am; t1 = a0; t2 = bm; t3 = b0; s0 = sa; s1 = sb; }
+		else {
+			const bool red_am = ((C.i0 + IA + Jm) & 1) == 0;          // (IA,Jm) and (IB,J0) share a colour
+			if (red_am) { t0 = am; t1 = b0; t2 = a0; t3 = bm; s0 = sb; s1 = sa; }   // (IA,J0) black, (IB,J0) red
+			else        { t0 = a0; t1 = bm; t2 = am; t3 = b0; s0 = sa; s1 = sb; }
 		}
 	}
+	double e0, e1;
+	if (MULTADD) {
+		// MatMultAdd: sum = u ; sum += term ...
+		e0 = add(add(u.x, t0), t1);
+		if (nt == 4) e0 = add(add(e0, t2), t3);
+		e1 = add(u.y, s0);
+		if (ns == 2) e1 = add(e1, s1);
+	} else {
+		// MatMult then VecAXPY(u, 1.0, rv)
+		e0 = add(t0, t1);
+		if (nt == 4) e0 = add(add(e0, t2), t3);
+		e1 = s0;
+		if (ns == 2) e1 = add(e1, s1);
+		e0 = add(u.x, mul(1.0, e0));
+		e1 = add(u.y, mul(1.0, e1));
+	}
 	double2 out;
-	if (MULTADD) { out.x = e0; out.y = e1; }
-	else { out.x = add(u.x, mul(1.0, e0)); out.y = add(u.y, mul(1.0, e1)); }
-	if (j0 >= F.nj) out.x = 0.0;
-	if (j0 + 1 >= F.nj) out.y = 0.0;
+	out.x = (j0 < F.nj) ? e0 : 0.0;
+	out.y = (j0 + 1 < F.nj) ? e1 : 0.0;
 	st2(uf + o, out);
 }

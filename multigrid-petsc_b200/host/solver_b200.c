@@ -105,7 +105,14 @@ void Assemble(Problem *prob, Mesh *mesh, Indices *indices, Operator *op, Solver 
 	cfg.nj = indices->level[0].grid[0].nj;
 	cfg.device = -1;
 	cfg.red_black_numbering = (map_style == 3);
+	/* row strips (B200 extension; replaces mpiexec -n P): -mgb_ranks P [-mgb_rank r] [-mgb_agglomerate n]
+	 * [-mgb_emulate 1: all strips in this process on one GPU, for tests] */
 	cfg.rank = 0; cfg.nranks = 1;
+	pbopt_get_int("-mgb_ranks", &cfg.nranks);
+	pbopt_get_int("-mgb_rank", &cfg.rank);
+	pbopt_get_int("-mgb_agglomerate", &cfg.agglomerate_below);
+	pbopt_get_int("-mgb_emulate", &cfg.emulate);
+	if (cfg.nranks > 1) want_csr = 0;
 	mgb_engine *e = NULL;
 	if (mgb_create(&cfg, &e) != MGB_OK) die("mgb_create");
 	set_engine(assem, e);

@@ -168,7 +168,7 @@ def b200_arm(a):
     if world > 1:
         from importlib import import_module
         strips = import_module("multigrid-petsc_b200.strips")
-        return strips.bench_strips(a, NPTS, LEVELS, ClockSampler, hbm_peak)
+        return strips.bench_strips(a, NPTS, LEVELS, ClockSampler, hbm_peak, options)
 
     n = NPTS - 2
     steps, warm = a.steps, max(a.warmup, 3)

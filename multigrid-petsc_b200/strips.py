@@ -1,0 +1,190 @@
+"""Row strips over several GPUs: one process per GPU (torchrun), torch.distributed only for the plumbing.
+
+The data path has no NCCL call: ghost rows, the gather of the first agglomerated level onto rank 0, the broadcast
+of its correction and the all-reduce of the norm partials are P2P stores into the peers' HBM followed by a flag
+(csrc/mgb_halo.cuh).  What this module does with torch.distributed is what mpiexec + PETSc's communicator setup do
+for the reference: rendezvous, the exchange of one 64-byte CUDA IPC handle per rank, barriers around timed regions
+and max-over-ranks of the measured times.
+"""
+import importlib
+import json
+import os
+import time
+
+import numpy as np
+
+_pkg = importlib.import_module("multigrid-petsc_b200")
+
+
+def init_distributed(backend=None):
+    """Join the torchrun rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def exchange_handles(mine):
+    """all-gather one bytes object per rank; returns their concatenation in rank order"""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, bytes(mine))
+    if any(len(h) != len(mine) for h in out):
+        raise _pkg.MgbError("ranks exported IPC handles of different sizes")
+    return b"".join(out)
+
+
+def connect(engine):
+    """Make the peers' arenas addressable: export, all-gather, import (collective)."""
+    engine.ipc_connect(exchange_handles(engine.ipc_export()))
+
+
+def strip_options(options, rank, world, agglomerate=0):
+    extra = f" -mgb_ranks {world} -mgb_rank {rank} -mgb_csr 0 -mgb_device {int(os.environ.get('LOCAL_RANK', rank))}"
+    if agglomerate:
+        extra += f" -mgb_agglomerate {agglomerate}"
+    return options + extra
+
+
+class StripSession(_pkg.Session):
+    """Session (host C layer: SetUpProblem .. Assemble) of this rank's strip, connected to its peers."""
+
+    def __init__(self, options, agglomerate=0):
+        self.rank, self.world = init_distributed()
+        super().__init__(strip_options(options, self.rank, self.world, agglomerate))
+        connect(self.engine)
+
+
+def gather_solution(engine, n, level=0, which=_pkg.VEC_U):
+    """Whole-grid solution on every rank, assembled from the per-rank rows (test / post-processing helper)."""
+    import torch
+    import torch.distributed as dist
+    u = engine.get_vec(which, level)                  # only the local rows are filled
+    r0, r1 = engine.local_rows(level)
+    rows = [None] * dist.get_world_size()
+    dist.all_gather_object(rows, (r0, r1, u[r0:r1].copy()))
+    full = np.zeros_like(u)
+    for a, b, part in rows:
+        full[a:b] = part
+    return full
+
+
+def _max_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
+    """bench.py at N > 1: the same 8193^2 V(3,3) workload split into N row strips (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = init_distributed("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n = npts - 2
+    steps, warm = a.steps, max(a.warmup, 3)
+    s = StripSession(options_fn(npts, levels, 1000))
+    e = s.engine
+    sm = _pkg.jacobi(0.8)
+    e.solve_vcycle(sm, 3, 3, max_iter=warm, rtol=0.0)
+    l0 = e.launch_count()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    it, rn, _ = e.solve_vcycle(sm, 3, 3, max_iter=steps, rtol=0.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = _max_over_ranks(e.last_solve_ms())
+    launches = _sum_over_ranks(e.launch_count() - l0)
+    t_end = time.time() + (0.0 if a.profile else 1.0)
+    k_busy = 0
+    while True:                                       # keep all ranks busy a little longer for the clock sampler
+        go = _max_over_ranks(1.0 if time.time() < t_end else 0.0)
+        if go == 0.0 or k_busy > 50:
+            break
+        e.solve_vcycle(sm, 3, 3, max_iter=steps, rtol=0.0)
+        k_busy += 1
+    clocks = clk.stop() if rank == 0 else None
+    value = steps / (ms * 1e-3)
+    # dominant kernel on this rank's strip (the launches include the ghost-row push: collective)
+    r0, r1 = e.local_rows(0)
+    t_j = _max_over_ranks(e.time_op("jacobi", 0, 20))
+    ach = 24.0 * n * n / (t_j * 1e-3) / 1e9          # aggregate over the N strips
+    peak, peak_kind = hbm_peak()
+    # e2e: every rank uploads its rows of the right-hand side from pinned memory and reads its rows of u back
+    b_host = torch.empty(n * n, dtype=torch.float64, pin_memory=True)
+    u_host = torch.empty(n * n, dtype=torch.float64, pin_memory=True)
+    x = np.linspace(0.0, 1.0, npts)[1:-1]
+    bh = b_host.numpy().reshape(n, n)
+    bh[r0:r1] = np.outer(np.sin(np.pi * x[r0:r1]), -2 * np.pi ** 2 * np.sin(np.pi * x))
+    bh[r0:r1] += 1e-3 * np.random.default_rng(r0).standard_normal((r1 - r0, n))
+    s.solve_rhs(b_host.data_ptr(), u_host.data_ptr())
+    nsolve, cycles = (1 if a.profile else 3), 0
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(nsolve):
+        r = s.solve_rhs(b_host.data_ptr(), u_host.data_ptr())
+        cycles += r["num_iter"]
+    torch.cuda.synchronize()
+    t_e2e = _max_over_ranks(time.perf_counter() - t0)
+    bytes_per_solve = 8.0 * n * n
+    s.close()
+    if rank == 0:
+        line = {"metric": "V-cycles/sec (fp64, 8193^2 grid)", "value": value, "unit": "V-cycles/s", "n_gpus": world,
+                "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"2D Poisson {npts}^2 fp64, {levels}-level V(3,3), Richardson+Jacobi 0.8 (BASELINE configs[3])",
+                           "unknowns": n * n, "l2": "inputs larger than L2 on every strip at N<=4; per-strip fine vector "
+                           f"{8.0 * n * n / world / 1e6:.0f} MB", "parallelism": f"{world} row strips, P2P ghost rows over NVLink, "
+                           "levels with <= 511 rows agglomerated on rank 0"},
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_stream5<ST_JACOBI> level 0 (+ ghost-row push)", "achieved": ach,
+                             "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world), "peak_kind": peak_kind + f" x {world} GPUs",
+                             "traffic": None, "vcycle_gbs_unfused_count": 264.0 * n * n * value / 1e9},
+                "e2e": {"value": cycles / t_e2e, "unit": "V-cycles/s", "h2d_bytes_per_step": bytes_per_solve * nsolve / cycles,
+                        "d2h_bytes_per_step": bytes_per_solve * nsolve / cycles, "solves": nsolve, "cycles_per_solve": cycles / nsolve,
+                        "note": "per solve: every rank uploads its rows of the rhs (pinned) + V-cycles to 1e-7 + reads its rows of u; "
+                                "bytes are totals over the ranks, per V-cycle"},
+                "gpu_launches": int(launches), "final_relative_residual": float(rn[-1])}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+def selfcheck(npts=1025, levels=10, expect_sha=None, expect_iters=None):
+    """Run under torchrun: solve the npts^2 case on WORLD_SIZE strips and compare with the 1-strip golden hash."""
+    import hashlib
+    import torch.distributed as dist
+    rank, world = init_distributed("nccl")
+    opts = (f"-npts {npts} -mesh 0 -iter 100000 -grids {levels} -levels {levels} -cycle 0 -map 2 -v 3,3 -moreNorm 0 "
+            "-pc_type jacobi -ksp_richardson_scale 0.8")
+    s = StripSession(opts)
+    it, rn, _ = s.engine.solve_vcycle(_pkg.jacobi(0.8), 3, 3, max_iter=100000, rtol=1e-7)
+    u = gather_solution(s.engine, npts - 2)
+    sha = hashlib.sha256(np.ascontiguousarray(u, dtype="<f8").tobytes()).hexdigest()
+    ok = (expect_sha is None or sha == expect_sha) and (expect_iters is None or it == expect_iters)
+    s.close()
+    if rank == 0:
+        print(json.dumps({"strips": world, "iters": it, "sha256": sha, "final": float(rn[-1]), "ok": bool(ok)}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1

@@ -97,7 +97,7 @@ def test_handle_exchange_world_size_2_gloo(tmp_path):
         assert f"-mgb_ranks {{world}} -mgb_rank {{rank}}" in opts and "-mgb_csr 0" in opts
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()
-        sys.stdout.write(f"ok{{rank}}\n"); sys.stdout.flush()
+        print("ok" + str(rank), flush=True)
     """))
     env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",

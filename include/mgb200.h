@@ -161,6 +161,8 @@ typedef struct {
 	int    max_iter;        /* -iter                                                             */
 	double rtol;            /* 1e-7 in the reference (src/solver.c:1530); extension knob -rtol   */
 	int    use_graph;       /* 1: replay the cycle as a CUDA graph (same kernels, same order)    */
+	int    no_fuse;         /* 1: one kernel per sweep / transfer (default 0: each leg of a level in one pass,
+	                           csrc/mgb_fused.cuh -- same arithmetic per value, bit-identical results)          */
 } mgb_vcycle_params;
 
 /* rnorm: max_iter+1 doubles; on return rnorm[0..num_iter] are the RELATIVE residual norms
@@ -178,6 +180,7 @@ typedef struct {
 	mgb_smoother level_smoother; int level_its;     /* -mg_levels_*                               */
 	int    coarse;           /* MGB_COARSE_*                                                      */
 	mgb_smoother coarse_smoother; int coarse_its;   /* -mg_coarse_*                               */
+	int    no_fuse;          /* as in mgb_vcycle_params                                            */
 } mgb_pcmg_params;
 /* reason: >0 converged (2 = rtol, 3 = atol, 4 = its), <0 diverged (PETSc KSPConvergedReason values) */
 int  mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *rnorm, int *num_iter, int *reason, double *seconds);

@@ -63,13 +63,13 @@ class Config(C.Structure):
 
 class VcycleParams(C.Structure):
     _fields_ = [("smoother", Smoother), ("v0", C.c_int), ("v1", C.c_int), ("max_iter", C.c_int),
-                ("rtol", C.c_double), ("use_graph", C.c_int)]
+                ("rtol", C.c_double), ("use_graph", C.c_int), ("no_fuse", C.c_int)]
 
 
 class PcmgParams(C.Structure):
     _fields_ = [("outer", C.c_int), ("rtol", C.c_double), ("abstol", C.c_double), ("dtol", C.c_double),
                 ("max_iter", C.c_int), ("level_smoother", Smoother), ("level_its", C.c_int), ("coarse", C.c_int),
-                ("coarse_smoother", Smoother), ("coarse_its", C.c_int)]
+                ("coarse_smoother", Smoother), ("coarse_its", C.c_int), ("no_fuse", C.c_int)]
 
 
 class RunResult(C.Structure):
@@ -302,17 +302,17 @@ class Engine:
         self._ck(self.L.mgb_op_aypx(self.h, yw, C.c_double(beta), xw, l))
 
     # solvers
-    def solve_vcycle(self, smoother, v0=3, v1=3, max_iter=100, rtol=1e-7, use_graph=True):
-        p = VcycleParams(smoother, v0, v1, max_iter, rtol, int(use_graph))
+    def solve_vcycle(self, smoother, v0=3, v1=3, max_iter=100, rtol=1e-7, use_graph=True, fuse=True):
+        p = VcycleParams(smoother, v0, v1, max_iter, rtol, int(use_graph), int(not fuse))
         rn = np.zeros(max_iter + 1)
         it, sec = C.c_int(), C.c_double()
         self._ck(self.L.mgb_solve_vcycle(self.h, C.byref(p), _pd(rn), C.byref(it), C.byref(sec)))
         return it.value, rn[: it.value + 1].copy(), sec.value
 
     def solve_pcmg(self, outer, level_smoother, level_its, coarse=COARSE_LU, coarse_smoother=None, coarse_its=1,
-                   rtol=1e-7, abstol=1e-50, dtol=1e4, max_iter=100):
+                   rtol=1e-7, abstol=1e-50, dtol=1e4, max_iter=100, fuse=True):
         cs = coarse_smoother if coarse_smoother is not None else jacobi(1.0)
-        p = PcmgParams(outer, rtol, abstol, dtol, max_iter, level_smoother, level_its, coarse, cs, coarse_its)
+        p = PcmgParams(outer, rtol, abstol, dtol, max_iter, level_smoother, level_its, coarse, cs, coarse_its, int(not fuse))
         rn = np.zeros(max_iter + 1)
         it, reason, sec = C.c_int(), C.c_int(), C.c_double()
         self._ck(self.L.mgb_solve_pcmg(self.h, C.byref(p), _pd(rn), C.byref(it), C.byref(reason), C.byref(sec)))

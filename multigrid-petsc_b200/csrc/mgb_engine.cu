@@ -27,6 +27,7 @@
 #include "mgb_csr.cuh"
 #include "mgb_coarse.cuh"
 #include "mgb_halo.cuh"
+#include "mgb_fused.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -214,7 +215,7 @@ extern "C" int mgb_strip_rows(const mgb_config *cfg, int level, int rank, int *r
 static LevelDev ldev(const mgb_engine *e, const Strip &s, int l)
 {
 	LevelDev d; d.ni = s.lev[l].ni; d.nj = e->geo[l].nj; d.pitch = e->geo[l].pitch; d.i0 = s.lev[l].r0;
-	d.uniform = e->geo[l].uniform; d.rb = e->cfg.red_black_numbering ? 1 : 0; d.coef = s.lev[l].coef;
+	d.uniform = e->geo[l].uniform; d.rb = e->cfg.red_black_numbering ? 1 : 0; d.coef = s.lev[l].coef; d.gni = e->geo[l].gni;
 	return d;
 }
 // view of rows [c0, c1) of a whole (agglomerated) level held in full on this strip
@@ -321,6 +322,8 @@ extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
 			if (S.present) CU(cudaMalloc(&S.coef, sizeof(double) * g.coef_host.size()));
 			const size_t blocks = (size_t)cdiv(g.pitch, MGB_SB_COLS) * (size_t)(S.ni / 2 + 1);
 			if (blocks > nb) nb = blocks;
+			const size_t fblocks = (size_t)(cdiv(g.pitch, FJ_VALID) + 1) * (size_t)(S.ni / 2 + 1);
+			if (fblocks > nb) nb = fblocks;
 		}
 		s.partial_cap = nb;
 		CU(cudaMalloc(&s.partial, sizeof(double) * nb));
@@ -571,7 +574,7 @@ static int gather_rows(mgb_engine *e, int l, int which)
 	return xfer_run(e, args, tot, chan);
 }
 
-// rows [rows[r]-1, rows[r+1]] of vector `which` on the first agglomerated level: rank 0 -> every rank
+// rows [rows[r]-3, rows[r+1]+3) of vector `which` on the first agglomerated level: rank 0 -> every rank
 static int bcast_rows(mgb_engine *e, int l, int which)
 {
 	if (e->P == 1) return MGB_OK;
@@ -585,7 +588,7 @@ static int bcast_rows(mgb_engine *e, int l, int which)
 		const int r = s.rank, k = S.phys[which];
 		if (r == 0) {
 			for (int q = 1; q < e->P; ++q) {
-				int c0 = e->geo[l].rows[q] - 1, c1 = e->geo[l].rows[q + 1] + 1;
+				int c0 = e->geo[l].rows[q] - 3, c1 = e->geo[l].rows[q + 1] + 3;   // the fused up-leg reads 3 coarse ghost rows
 				if (c0 < 0) c0 = 0;
 				if (c1 > e->geo[l].gni) c1 = e->geo[l].gni;
 				const int d = a.ndst++;
@@ -1046,6 +1049,97 @@ static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 	return halo(e, l, xv, 2);
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused legs (Jacobi)
+#define HALO_DEPTH (MGB_GHOST_ROWS - 1)
+
+template <int D, int PRE, int POST>
+static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st) { k_jfused<D, PRE, POST><<<grid, FJ_THREADS, 0, st>>>(a); }
+
+template <int D>
+static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cudaStream_t st)
+{
+#define JF(PRE_, POST_) if (pre == PRE_ && post == POST_) { launch_jfused<D, PRE_, POST_>(a, grid, st); return MGB_OK; }
+	JF(PRE_GIVEN, POST_NONE) JF(PRE_GIVEN, POST_RESTRICT) JF(PRE_GIVEN, POST_NORM)
+	JF(PRE_ZERO, POST_NONE) JF(PRE_ZERO, POST_RESTRICT) JF(PRE_ZERO, POST_NORM)
+	JF(PRE_PROLONG, POST_NONE) JF(PRE_PROLONG, POST_NORM)
+	JF(PRE_PROLONG_MULTADD, POST_NONE) JF(PRE_PROLONG_MULTADD, POST_NORM)
+#undef JF
+	return fail(MGB_EINVAL, "fused kernel: combination pre %d / post %d not built", pre, post);
+}
+
+// rows per block of the fused kernel: as many as keep >= ~2 blocks per SM, between 16 and 256, even
+static int pick_rows(const LevelGeom &g, int ni)
+{
+	const long long tiles = cdiv(g.pitch, FJ_VALID);
+	long long r = (long long)ni * tiles / 592;
+	if (r > 256) r = 256;
+	if (r < 16) r = 16;
+	return (int)(r & ~1LL);
+}
+
+static bool fusable(const mgb_engine *e, const mgb_smoother *sm) { return sm->type == MGB_SMOOTH_JACOBI && !e->cfg.red_black_numbering; }
+
+// One leg on level l: [x += pro * u[l+1]] -> `its` Jacobi sweeps on (b = bv, x = xv) -> [b[l+1] = res * (b - A x)] or
+// [scal[norm_slot] = ||b - A x||].  Sweeps beyond 4 are chained as extra passes.  On return the iterate is in v[xv]
+// with valid ghost rows; a restricted right-hand side has been exchanged / gathered.
+static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int pre, int post, int bv, int xv, int sv, int norm_slot)
+{
+	const LevelGeom &g = e->geo[l];
+	if (its < 1) return fail(MGB_EINVAL, "fused leg needs at least one sweep");
+	int done = 0;
+	while (done < its) {
+		const int D = (its - done > 4) ? 4 : its - done;
+		const bool firstc = done == 0, lastc = done + D == its;
+		const int pre_k = firstc ? pre : PRE_GIVEN, post_k = lastc ? post : POST_NONE;
+		std::vector<int> nb;
+		for (auto &s : e->strips) {
+			if (!computes(s, l)) continue;
+			SLevel &S = s.lev[l];
+			FusedArgs a; memset(&a, 0, sizeof a);
+			a.u_in = S.v[xv]; a.b = S.v[bv]; a.u_out = S.v[sv];
+			a.F = ldev(e, s, l); a.scale = sm->scale; a.gni = g.gni;
+			a.rows = pick_rows(g, S.ni);
+			a.R3 = e->R3; a.P3 = e->P3;
+			int tiles = cdiv(g.pitch, FJ_VALID);
+			if (pre_k == PRE_PROLONG || pre_k == PRE_PROLONG_MULTADD) {
+				size_t coff; a.C = coarse_view(e, s, l + 1, g.dist, &coff);
+				a.uc = s.lev[l + 1].v[MGB_VEC_U] + coff;
+			}
+			if (post_k == POST_RESTRICT) {
+				size_t coff; a.C = coarse_view(e, s, l + 1, g.dist, &coff);
+				a.bc = s.lev[l + 1].v[MGB_VEC_B] + coff;
+				const int need = cdiv(2 * e->geo[l + 1].pitch, FJ_VALID);
+				if (need > tiles) tiles = need;
+			}
+			dim3 grid(tiles, cdiv(S.ni, a.rows));
+			if (post_k == POST_NORM) {
+				if ((size_t)grid.x * grid.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
+				a.partial = s.partial;
+				nb.push_back((int)(grid.x * grid.y));
+			}
+			int rc;
+			switch (D) {
+			case 1: rc = dispatch_jfused<1>(pre_k, post_k, a, grid, s.stream); break;
+			case 2: rc = dispatch_jfused<2>(pre_k, post_k, a, grid, s.stream); break;
+			case 3: rc = dispatch_jfused<3>(pre_k, post_k, a, grid, s.stream); break;
+			default: rc = dispatch_jfused<4>(pre_k, post_k, a, grid, s.stream); break;
+			}
+			TRY(rc);
+			LAUNCHED(e); KCHECK();
+		}
+		swap_vec(e, l, xv, sv);
+		TRY(halo(e, l, xv, HALO_DEPTH));
+		if (post_k == POST_RESTRICT) {
+			if (e->geo[l + 1].dist) TRY(halo(e, l + 1, MGB_VEC_B, HALO_DEPTH));
+			else if (g.dist) TRY(gather_rows(e, l + 1, MGB_VEC_B));
+		}
+		if (post_k == POST_NORM) TRY(reduce_tail(e, l, nb, norm_slot, 1));
+		done += D;
+	}
+	return MGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ single ops (C-ABI)
 // The single operations are collective in a multi-rank run.  They refresh the ghost rows of their inputs first
 // (vectors may have been set from the host); the solvers keep ghosts valid incrementally.
@@ -1189,6 +1283,25 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 {
 	const int Lc = e->L;
 	const mgb_smoother *s = &p->smoother;
+	if (!p->no_fuse && fusable(e, s) && p->v0 >= 1 && (Lc == 1 || p->v1 >= 1)) {
+		// the same cycle with each leg of a level done in one pass (mgb_fused.cuh): identical arithmetic per value
+		const int B = MGB_VEC_B, U = MGB_VEC_U, W = MGB_VEC_W;
+		if (Lc == 1) {
+			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_NORM, B, U, W, 0));
+		} else {
+			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));      // :1531-1535
+			for (int l = 1; l < Lc - 1; ++l)
+				TRY(fused_leg(e, l, s, p->v0, PRE_ZERO, POST_RESTRICT, B, U, W, 0));                     // :1534-1536
+			TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0));                         // :1536 coarsest
+			for (int l = Lc - 2; l >= 0; --l) {
+				if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(bcast_rows(e, l + 1, U));
+				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0));  // :1540-1546
+			}
+		}
+		Strip &s0 = e->strips[0];
+		CU(cudaMemcpyAsync(s0.scal_host, s0.scal, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+		return MGB_OK;
+	}
 	TRY(smooth(e, 0, s, p->v0, first, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));                          // :1531-1532
 	for (int l = 1; l < Lc; ++l) {
 		TRY(restrict_to_coarse(e, l - 1, MGB_VEC_B, MGB_VEC_U, MGB_VEC_R, true));                 // :1534-1535
@@ -1232,7 +1345,7 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 	if (p->v0 < 0 || p->v1 < 0 || p->max_iter < 0) return fail(MGB_EINVAL, "negative sweep or iteration count");
 	Strip &s0 = e->strips[0];
 	// bnorm = ||b0|| ; u0 = 0 ; rnorm[0] = ||A0 u0 - b0||                                      (:1512-1520)
-	GHOSTS(e, 0, MGB_VEC_B);
+	TRY(halo(e, 0, MGB_VEC_B, HALO_DEPTH));
 	TRY(k_reduce(e, 0, MGB_VEC_B, -1, 1, 1));
 	TRY(vec_zero(e, MGB_VEC_U, 0));
 	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));
@@ -1296,14 +1409,24 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 {
 	const int Lc = e->L;
 	if (l == Lc - 1) {
-		if (p->coarse == MGB_COARSE_RICHARDSON)
+		if (p->coarse == MGB_COARSE_RICHARDSON) {
+			if (!p->no_fuse && fusable(e, &p->coarse_smoother) && p->coarse_its >= 1)
+				return fused_leg(e, l, &p->coarse_smoother, p->coarse_its, PRE_ZERO, POST_NONE, bv, xv, MGB_VEC_W, 0);
 			return smooth(e, l, &p->coarse_smoother, p->coarse_its, true, bv, xv, MGB_VEC_W);
+		}
 		for (auto &s : e->strips) {
 			if (!computes(s, l)) continue;
 			SLevel &S = s.lev[l];
 			if (bandlu_solve(S.lu, S.v[bv], S.v[xv], S.ni, e->geo[l].nj, e->geo[l].pitch, s.stream)) return fail(MGB_ECUDA, "coarse LU solve launch failed");
 			LAUNCHED(e);
 		}
+		return MGB_OK;
+	}
+	if (!p->no_fuse && fusable(e, &p->level_smoother) && p->level_its >= 1) {
+		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_ZERO, POST_RESTRICT, bv, xv, MGB_VEC_W, 0));
+		TRY(pcmg_cycle(e, p, l + 1, MGB_VEC_B, MGB_VEC_U));
+		if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(bcast_rows(e, l + 1, MGB_VEC_U));
+		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_PROLONG_MULTADD, POST_NONE, bv, xv, MGB_VEC_W, 0));
 		return MGB_OK;
 	}
 	TRY(smooth(e, l, &p->level_smoother, p->level_its, true, bv, xv, MGB_VEC_W));     // pre-smooth from x = 0
@@ -1358,7 +1481,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 	for (int i = 0; i <= p->max_iter; ++i) rnorm[i] = NAN;
 	double *hs = host_scal(e);
 	// z = B r : one multigrid cycle on (r, z); the ghost rows of r are refreshed first (the restriction reads them)
-	auto precond = [&]() -> int { TRY(halo(e, 0, R, 2)); return pcmg_cycle(e, p, 0, R, Z); };
+	auto precond = [&]() -> int { TRY(halo(e, 0, R, HALO_DEPTH)); return pcmg_cycle(e, p, 0, R, Z); };
 
 	TRY(vec_zero(e, X, 0));                                  // KSPSolve: zero initial guess
 	TRY(k_vecop<2>(e, 0, R, B, 0.0));                        // r = b

@@ -365,3 +365,26 @@ def test_strip_configuration_errors():
         mgb.Engine(4, 127, nranks=8, emulate=True, agglomerate_below=31)  # strips too thin
     with pytest.raises(mgb.MgbError):
         mgb.Engine(4, 127, nranks=2, emulate=True, agglomerate_below=127) # nothing to distribute
+
+
+# ------------------------------------------------------------------ fused legs (temporal blocking) == one kernel per sweep
+@pytest.mark.parametrize("opts", [
+    base(129, 4) + " " + JAC, base(129, 7, v="2,1") + " " + JAC, base(129, 7, v="1,4") + " " + JAC,
+    base(129, 5, v="4,2") + " " + JAC, base(129, 4, v="6,9", it=200) + " " + JAC, base(101, 3) + " " + JAC,
+    base(65, 4, mesh=1, it=400) + " " + JAC, base(65, 4, mesh=2, it=400) + " " + JAC, base(17, 1, it=50) + " " + JAC,
+    base(1025, 10) + " " + JAC, base(513, 3, it=30) + " " + JAC,
+    base(129, 7, cycle=8) + " -ksp_type cg -ksp_rtol 1e-10 -mg_levels_ksp_type richardson -mg_levels_pc_type jacobi "
+    "-mg_levels_ksp_richardson_scale 0.8 -mg_levels_ksp_max_it 3",
+    base(257, 4, cycle=8, it=60) + " -ksp_type richardson -mg_levels_ksp_type richardson -mg_levels_pc_type jacobi "
+    "-mg_levels_ksp_richardson_scale 0.7 -mg_levels_ksp_max_it 2 -mg_coarse_ksp_type richardson -mg_coarse_pc_type jacobi "
+    "-mg_coarse_ksp_richardson_scale 0.8 -mg_coarse_ksp_max_it 7"])
+@pytest.mark.parametrize("ranks", [1, 2])
+def test_fused_legs_bit_identical_to_unfused(opts, ranks):
+    extra = "" if ranks == 1 else f" -mgb_ranks {ranks} -mgb_emulate 1 -mgb_agglomerate 31"
+    if ranks > 1 and ("-npts 17 " in opts):
+        pytest.skip("nothing to distribute")
+    a = mgb.run_poisson(opts + extra + " -mgb_fuse 1")
+    b = mgb.run_poisson(opts + " -mgb_fuse 0")
+    assert a["num_iter"] == b["num_iter"]
+    assert a["u"].tobytes() == b["u"].tobytes()
+    assert np.allclose(a["rnorm"], b["rnorm"], rtol=1e-12, atol=RNORM_ATOL, equal_nan=True)

@@ -1051,7 +1051,7 @@ static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 
 
 // ------------------------------------------------------------------------------------------------ fused legs (Jacobi)
-#define HALO_DEPTH (MGB_GHOST_ROWS - 1)
+#define HALO_DEPTH MGB_GHOST_ROWS
 
 template <int D, int PRE, int POST>
 static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st) { k_jfused<D, PRE, POST><<<grid, FJ_THREADS, 0, st>>>(a); }

@@ -193,7 +193,9 @@ long long mgb_launch_count(const mgb_engine *e);
 double mgb_last_solve_ms(const mgb_engine *e);
 /* time `reps` back-to-back launches of one operation with CUDA events on the engine's stream;
  * op: 0 apply, 1 residual, 2 jacobi sweep, 3 red-black full sweep (2 half sweeps), 4 fused residual+restrict,
- * 5 prolong+correct, 6 residual norm, 7 csr spmv (A), 8 nrm2, 9 dot, 10 axpy.  ms_per_launch is the average. */
+ * 5 prolong+correct, 6 residual norm, 7 csr spmv (A), 8 nrm2, 9 dot, 10 axpy; fused legs (mgb_fused.cuh):
+ * 11 down leg (3 sweeps + residual + restriction), 12 up leg (prolongation + 3 sweeps + residual norm),
+ * 13 three sweeps, 14 one sweep, 15 down leg from a zero guess.  ms_per_launch is the average. */
 int  mgb_time_op(mgb_engine *e, int op, int level, int reps, double *ms_per_launch);
 
 #ifdef __cplusplus

@@ -32,7 +32,12 @@ COARSE_LU, COARSE_RICHARDSON = 0, 1
 # mgb_time_op codes and their algorithmic HBM bytes per (fine) unknown (SURVEY.md 8d / DESIGN.md)
 OPS = {"apply": (0, 16), "residual": (1, 24), "jacobi": (2, 24), "rbsor_full": (3, 48), "residual_restrict": (4, 18),
        "prolong_correct": (5, 18), "residual_norm": (6, 16), "csr_spmv": (7, 80), "nrm2": (8, 8), "dot": (9, 16),
-       "axpy": (10, 24)}
+       "axpy": (10, 24),
+       # fused legs: bytes of the UNFUSED sequence they replace (3 x 24 + 18, 18 + 3 x 24 + 16, 3 x 24, 24, 16 + 2 x 24 + 18)
+       # and, second number, their own compulsory traffic (read u, b; write u; +2 coarse)
+       "fused_down": (11, 90), "fused_up": (12, 106), "fused_3sweeps": (13, 72), "fused_1sweep": (14, 24),
+       "fused_down_zero": (15, 82)}
+FUSED_OWN_BYTES = {"fused_down": 26, "fused_up": 26, "fused_3sweeps": 24, "fused_1sweep": 24, "fused_down_zero": 18}
 
 
 class MgbError(RuntimeError):

@@ -1081,7 +1081,7 @@ static int pick_rows(const LevelGeom &g, int ni)
 static bool fusable(const mgb_engine *e, const mgb_smoother *sm) { return sm->type == MGB_SMOOTH_JACOBI && !e->cfg.red_black_numbering; }
 
 // One leg on level l: [x += pro * u[l+1]] -> `its` Jacobi sweeps on (b = bv, x = xv) -> [b[l+1] = res * (b - A x)] or
-// [scal[norm_slot] = ||b - A x||].  Sweeps beyond 4 are chained as extra passes.  On return the iterate is in v[xv]
+// [scal[norm_slot] = ||b - A x||].  Sweeps beyond FJ_MAXD are chained as extra passes.  On return the iterate is in v[xv]
 // with valid ghost rows; a restricted right-hand side has been exchanged / gathered.
 static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int pre, int post, int bv, int xv, int sv, int norm_slot)
 {
@@ -1089,7 +1089,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 	if (its < 1) return fail(MGB_EINVAL, "fused leg needs at least one sweep");
 	int done = 0;
 	while (done < its) {
-		const int D = (its - done > 4) ? 4 : its - done;
+		const int D = (its - done > FJ_MAXD) ? FJ_MAXD : its - done;
 		const bool firstc = done == 0, lastc = done + D == its;
 		const int pre_k = firstc ? pre : PRE_GIVEN, post_k = lastc ? post : POST_NONE;
 		std::vector<int> nb;
@@ -1122,8 +1122,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			switch (D) {
 			case 1: rc = dispatch_jfused<1>(pre_k, post_k, a, grid, s.stream); break;
 			case 2: rc = dispatch_jfused<2>(pre_k, post_k, a, grid, s.stream); break;
-			case 3: rc = dispatch_jfused<3>(pre_k, post_k, a, grid, s.stream); break;
-			default: rc = dispatch_jfused<4>(pre_k, post_k, a, grid, s.stream); break;
+			default: rc = dispatch_jfused<3>(pre_k, post_k, a, grid, s.stream); break;
 			}
 			TRY(rc);
 			LAUNCHED(e); KCHECK();
@@ -1562,7 +1561,7 @@ extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *m
 	if (e->strips.size() != 1) return fail(MGB_EINVAL, "mgb_time_op times one strip per process");
 	mgb_smoother jac = {MGB_SMOOTH_JACOBI, 0.8, 1.0, 0, 1};
 	const bool has_coarse = level + 1 < e->L;
-	if ((op == 4 || op == 5) && !has_coarse) return fail(MGB_EINVAL, "level %d has no coarser level", level);
+	if ((op == 4 || op == 5 || op == 11 || op == 12 || op == 15) && !has_coarse) return fail(MGB_EINVAL, "level %d has no coarser level", level);
 	if (op == 7 && !e->csr_built) return fail(MGB_ESTATE, "mgb_assemble_csr was not called");
 	TRY(set_sor_omega(e, 1.0));
 	Strip &s = e->strips[0];
@@ -1583,6 +1582,11 @@ extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *m
 			case 8: TRY(k_reduce(e, level, U, -1, 0, 1)); break;
 			case 9: TRY(k_reduce(e, level, U, B, 0, 0)); break;
 			case 10: TRY(k_vecop<0>(e, level, R, U, 0.5)); break;
+			case 11: TRY(fused_leg(e, level, &jac, 3, PRE_GIVEN, POST_RESTRICT, B, U, MGB_VEC_W, 0)); break;
+			case 12: TRY(fused_leg(e, level, &jac, 3, PRE_PROLONG, POST_NORM, B, U, MGB_VEC_W, 0)); break;
+			case 13: TRY(fused_leg(e, level, &jac, 3, PRE_GIVEN, POST_NONE, B, U, MGB_VEC_W, 0)); break;
+			case 14: TRY(fused_leg(e, level, &jac, 1, PRE_GIVEN, POST_NONE, B, U, MGB_VEC_W, 0)); break;
+			case 15: TRY(fused_leg(e, level, &jac, 3, PRE_ZERO, POST_RESTRICT, B, U, MGB_VEC_W, 0)); break;
 			default: return fail(MGB_EINVAL, "unknown op %d", op);
 			}
 		}

@@ -11,15 +11,20 @@
 // Every value is produced by exactly the same sequence of IEEE operations as in the one-sweep kernels
 // (mgb_stencil.cuh / mgb_transfer.cuh), so the results are bit-identical; only the order in which points are
 // visited changes.  A block owns a tile of FJ_VALID columns x `rows` rows and streams down the rows.  Each thread
-// owns two adjacent columns and keeps, for every stage s = 0..D (stage 0 = input, stage s = after s sweeps), a
-// three-row register window; stage s of row t-s is computed at step t from stage s-1 of rows t-s-1 .. t-s+1.
+// owns two adjacent columns and keeps, for every stage s = 0..D (stage 0 = input, stage s = after s sweeps), the
+// last three rows in registers; stage s of row t-s is computed at step t from stage s-1 of rows t-s-1 .. t-s+1.
 // West/east neighbours of the centre row come from a double-buffered shared-memory copy of the rows produced in
 // the previous step (one __syncthreads per step).  FJ_HALO columns on each side of the tile and D+2 rows above
 // and below it are recomputed redundantly; values outside the global grid are forced to zero at every stage,
 // exactly like the pad columns / ghost rows of the one-sweep kernels.
 //
+// Instruction economy (the kernel is issue / fp64-pipe bound, not HBM bound): all row histories are rings of FOUR
+// slots indexed by (row & 3) and the row loop is unrolled by four with the step number modulo 4 as a template
+// parameter, so ring positions are compile-time register names -- no register-to-register moves; blocks whose
+// tile and halo lie strictly inside the grid run a variant without the out-of-grid masks.
+//
 // Strips: rows in the ghost zone that belong to a neighbour are recomputed from ghost data, which therefore has
-// to be valid to depth D+2 (u) / D+1 (b) on entry -- MGB_GHOST_ROWS = 6 covers D <= 4.
+// to be valid to depth D+2 (u) / D+1 (b) on entry -- MGB_GHOST_ROWS = 6 covers D <= 3 (+ the unroll round-down).
 #pragma once
 #include "mgb_common.cuh"
 #include "mgb_transfer.cuh"
@@ -28,7 +33,7 @@
 #define FJ_COLS (2 * FJ_THREADS)
 #define FJ_HALO 6
 #define FJ_VALID (FJ_COLS - 2 * FJ_HALO)
-#define FJ_PF 2                                   // rows of u / b requested ahead of their use
+#define FJ_MAXD 3
 
 enum { PRE_GIVEN = 0, PRE_ZERO = 1, PRE_PROLONG = 2, PRE_PROLONG_MULTADD = 3 };
 enum { POST_NONE = 0, POST_RESTRICT = 1, POST_NORM = 2 };
@@ -58,18 +63,18 @@ __device__ __forceinline__ Coef load_coef(const LevelDev &L, int gni, int grow)
 
 // u + pro * uc at fine row i (local), columns j0, j0+1 -- the arithmetic of k_prolong_add, natural numbering
 template <int MULTADD>
-__device__ __forceinline__ double2 prolonged(double2 u, const double *__restrict__ uc, int i, int j0, size_t PC, const Stencil3 &Pw)
+__device__ __forceinline__ double2 prolonged(double2 u, const double *__restrict__ uc, int i, int j0, ptrdiff_t PC, const Stencil3 &Pw)
 {
 	const int J0 = j0 >> 1, Jm = J0 - 1;
 	double e0, e1;
 	if (i & 1) {
-		const double *c = uc + (ptrdiff_t)((i - 1) >> 1) * (ptrdiff_t)PC;
+		const double *c = uc + (ptrdiff_t)((i - 1) >> 1) * PC;
 		const double cm = mul(Pw.w[3 + 2], c[Jm]), c0 = mul(Pw.w[3 + 0], c[J0]);
 		const double s0 = mul(Pw.w[3 + 1], c[J0]);
 		if (MULTADD) { e0 = add(add(u.x, cm), c0); e1 = add(u.y, s0); }
 		else { e0 = add(u.x, mul(1.0, add(cm, c0))); e1 = add(u.y, mul(1.0, s0)); }
 	} else {
-		const double *cA = uc + (ptrdiff_t)((i >> 1) - 1) * (ptrdiff_t)PC;
+		const double *cA = uc + (ptrdiff_t)((i >> 1) - 1) * PC;
 		const double *cB = cA + PC;
 		const double am = mul(Pw.w[6 + 2], cA[Jm]), a0 = mul(Pw.w[6 + 0], cA[J0]);
 		const double bm = mul(Pw.w[0 + 2], cB[Jm]), b0 = mul(Pw.w[0 + 0], cB[J0]);
@@ -80,6 +85,188 @@ __device__ __forceinline__ double2 prolonged(double2 u, const double *__restrict
 	return make_double2(e0, e1);
 }
 
+// per-thread state: rings of four slots, slot = row & 3
+template <int D>
+struct JfState {
+	double2 win[D + 1][4];   // win[s][row & 3]: stage s of that row (rows t-s-2 .. t-s live)
+	double2 bq[4];           // b of rows t-4 .. t-1
+	double rw[4][3];         // POST_RESTRICT: residual row (own .x, own .y, east neighbour)
+	double2 upf[2], bpf[2];  // requested rows: u of rows t, t+1 ; b of rows t-1, t
+	double acc;
+};
+
+struct JfBlock {
+	int tid, c0, j0, y0, y1;
+	ptrdiff_t P;
+	bool in0, in1, ld_ok, st_ok;
+	Coef cu;                 // coefficients of a uniform operator, held in ordinary (per-thread) registers
+	double scale;
+};
+
+// The stencil coefficients are warp-uniform; left to itself the compiler parks them in uniform registers and copies
+// them into vector registers in front of every DMUL/DADD (fp64 instructions take no uniform operands): ~45 extra
+// instructions per row step.  Passing them through an opaque asm makes them ordinary per-thread values.
+__device__ __forceinline__ double vreg(double x) { double y; asm volatile("mov.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+
+// one row step; K = t & 3 (compile time), MASK = the block touches the outside of the grid
+template <int D, int PRE, int POST, bool MASK, bool UNI, int K>
+__device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, JfState<D> &S, double (*sh)[D + 2][FJ_COLS + 4], int t)
+{
+	const LevelDev &F = A.F;
+	constexpr int par = K & 1;
+	double (*shp)[FJ_COLS + 4] = sh[par ^ 1];            // rows published in the previous step
+	double (*shn)[FJ_COLS + 4] = sh[par];
+	const int tid = B.tid;
+	auto row_ok = [&](int i) {
+		if (!MASK) return true;
+		const int g = F.i0 + i;
+		return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
+	};
+	// ---- stage 0 of row t and b of row t-1 arrive; rows t+2 / t+1 are requested
+	double2 u0 = S.upf[K & 1];
+	S.bq[(K + 3) & 3] = S.bpf[K & 1];                     // slot of row t-1
+	if (PRE != PRE_ZERO) {
+		if (!MASK || (B.ld_ok && row_ok(t + 2))) S.upf[K & 1] = ld2(A.u_in + (ptrdiff_t)(t + 2) * B.P + B.j0);
+		else S.upf[K & 1] = make_double2(0.0, 0.0);
+	}
+	if (!MASK || (B.ld_ok && row_ok(t + 1))) S.bpf[K & 1] = ld2(A.b + (ptrdiff_t)(t + 1) * B.P + B.j0);
+	else S.bpf[K & 1] = make_double2(0.0, 0.0);
+	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
+		if (!MASK || (B.ld_ok && row_ok(t)))
+			u0 = prolonged<PRE == PRE_PROLONG_MULTADD>(u0, A.uc, t, B.j0, (ptrdiff_t)A.C.pitch, A.P3);
+	}
+	if (MASK) {
+		const bool rk = row_ok(t);
+		if (!B.in0 || !rk) u0.x = 0.0;
+		if (!B.in1 || !rk) u0.y = 0.0;
+	}
+	if (PRE == PRE_ZERO) u0 = make_double2(0.0, 0.0);
+	S.win[0][K] = u0;
+	// ---- stage s of row t-s
+#pragma unroll
+	for (int s = 1; s <= D; ++s) {
+		const int c = t - s;
+		const int g = F.i0 + c;
+		Coef cf = B.cu;
+		if (!UNI) cf = load_coef(F, A.gni, g);
+		const double2 bb = S.bq[(K - s) & 3];             // b of row t-s
+		double2 o;
+		if (PRE == PRE_ZERO && s == 1) {
+			// first Richardson iteration from a zero guess: r = b, x = 0 + scale * (r * dinv)
+			o.x = mul(B.scale, mul(bb.x, cf.dinv));
+			o.y = mul(B.scale, mul(bb.y, cf.dinv));
+		} else {
+			const double2 xm = S.win[s - 1][(K - s - 1) & 3], xc = S.win[s - 1][(K - s) & 3], xn = S.win[s - 1][(K - s + 1) & 3];
+			const double xw = shp[s - 1][2 * tid + 1];    // column j0-1
+			const double xe = shp[s - 1][2 * tid + 4];    // column j0+2
+			const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, xw, xc.x, xc.y, xn.x);
+			const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, xe, xn.y);
+			const double r0 = sub(bb.x, t0), r1 = sub(bb.y, t1);
+			o.x = add(xc.x, mul(B.scale, mul(r0, cf.dinv)));
+			o.y = add(xc.y, mul(B.scale, mul(r1, cf.dinv)));
+		}
+		if (MASK) {
+			const bool rok = g >= 0 && g < A.gni;
+			if (!B.in0 || !rok) o.x = 0.0;
+			if (!B.in1 || !rok) o.y = 0.0;
+		}
+		S.win[s][(K - s) & 3] = o;
+	}
+	// ---- the finished row t-D
+	{
+		const int c = t - D;
+		if (B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
+	}
+	// ---- residual of row rho = t-D-1 from stage D
+	double2 res = make_double2(0.0, 0.0);
+	if (POST != POST_NONE) {
+		const int rho = t - D - 1;
+		const int g = F.i0 + rho;
+		Coef cf = B.cu;
+		if (!UNI) cf = load_coef(F, A.gni, g);
+		const double2 xm = S.win[D][(K - D - 2) & 3], xc = S.win[D][(K - D - 1) & 3], xn = S.win[D][(K - D) & 3];
+		const double xw = shp[D][2 * tid + 1];
+		const double xe = shp[D][2 * tid + 4];
+		const double2 bb = S.bq[(K - D - 1) & 3];
+		const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, xw, xc.x, xc.y, xn.x);
+		const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, xe, xn.y);
+		res.x = sub(bb.x, t0); res.y = sub(bb.y, t1);
+		if (MASK) {
+			const bool rok = g >= 0 && g < A.gni;
+			if (!B.in0 || !rok) res.x = 0.0;
+			if (!B.in1 || !rok) res.y = 0.0;
+		}
+		if (POST == POST_NORM) {
+			if (B.st_ok && rho >= B.y0 && rho < B.y1) S.acc += res.x * res.x + res.y * res.y;
+		}
+	}
+	// ---- restriction of the residual rows completed in the previous step (their east neighbours are visible now)
+	if (POST == POST_RESTRICT) {
+		constexpr int RP = (K - D - 2) & 3;               // slot of row rp = t-D-2
+		S.rw[RP][2] = shp[D + 1][2 * tid + 4];            // column j0+2 of row rp
+		if ((((K - D - 2) & 1) == 0)) {
+			const int rp = t - D - 2;
+			const int I = (rp >> 1) - 1;                   // coarse row (local) fed by fine rows rp-2 .. rp
+			const int J = B.j0 >> 1;
+			if (B.st_ok && I >= (B.y0 >> 1) && I < (B.y1 >> 1) && I < A.C.ni && J < A.C.pitch) {
+				constexpr int R0 = (RP + 2) & 3, R1 = (RP + 3) & 3;    // rows rp-2, rp-1
+				double sum = mul(A.R3.w[0], S.rw[R0][0]);
+				sum = add(sum, mul(A.R3.w[1], S.rw[R0][1]));
+				sum = add(sum, mul(A.R3.w[2], S.rw[R0][2]));
+				sum = add(sum, mul(A.R3.w[3], S.rw[R1][0]));
+				sum = add(sum, mul(A.R3.w[4], S.rw[R1][1]));
+				sum = add(sum, mul(A.R3.w[5], S.rw[R1][2]));
+				sum = add(sum, mul(A.R3.w[6], S.rw[RP][0]));
+				sum = add(sum, mul(A.R3.w[7], S.rw[RP][1]));
+				sum = add(sum, mul(A.R3.w[8], S.rw[RP][2]));
+				A.bc[(size_t)I * A.C.pitch + J] = (J < A.C.nj) ? sum : 0.0;
+			}
+		}
+		S.rw[(K - D - 1) & 3][0] = res.x; S.rw[(K - D - 1) & 3][1] = res.y;
+	}
+	// ---- publish the rows produced in this step
+#pragma unroll
+	for (int s = 0; s <= D; ++s) *reinterpret_cast<double2 *>(&shn[s][2 * tid + 2]) = S.win[s][(K - s) & 3];
+	if (POST != POST_NONE) *reinterpret_cast<double2 *>(&shn[D + 1][2 * tid + 2]) = res;
+	__syncthreads();
+}
+
+template <int D, int PRE, int POST, bool MASK, bool UNI>
+__device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, double (*sh)[D + 2][FJ_COLS + 4], int t0, int t1)
+{
+	JfState<D> S;
+#pragma unroll
+	for (int s = 0; s <= D; ++s)
+#pragma unroll
+		for (int k = 0; k < 4; ++k) S.win[s][k] = make_double2(0.0, 0.0);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) { S.bq[k] = make_double2(0.0, 0.0); S.rw[k][0] = 0.0; S.rw[k][1] = 0.0; S.rw[k][2] = 0.0; }
+	S.acc = 0.0;
+	const LevelDev &F = A.F;
+	auto row_ok = [&](int i) {
+		if (!MASK) return true;
+		const int g = F.i0 + i;
+		return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
+	};
+	// requests for the first two steps (t0 is a multiple of 4: slots 0, 1)
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		S.upf[k] = (PRE != PRE_ZERO && (!MASK || (B.ld_ok && row_ok(t0 + k)))) ? ld2(A.u_in + (ptrdiff_t)(t0 + k) * B.P + B.j0) : make_double2(0.0, 0.0);
+		// bpf[k & 1] at step t holds b of row t-1: steps t0, t0+1 consume rows t0-1, t0
+		S.bpf[k] = (!MASK || (B.ld_ok && row_ok(t0 - 1 + k))) ? ld2(A.b + (ptrdiff_t)(t0 - 1 + k) * B.P + B.j0) : make_double2(0.0, 0.0);
+	}
+	for (int t = t0; t <= t1; t += 4) {
+		jf_step<D, PRE, POST, MASK, UNI, 0>(A, B, S, sh, t);
+		jf_step<D, PRE, POST, MASK, UNI, 1>(A, B, S, sh, t + 1);
+		jf_step<D, PRE, POST, MASK, UNI, 2>(A, B, S, sh, t + 2);
+		jf_step<D, PRE, POST, MASK, UNI, 3>(A, B, S, sh, t + 3);
+	}
+	if (POST == POST_NORM) {
+		const double s = block_sum<FJ_THREADS>(S.acc);
+		if (B.tid == 0) A.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+	}
+}
+
 template <int D, int PRE, int POST>
 __global__ void __launch_bounds__(FJ_THREADS)
 k_jfused(FusedArgs A)
@@ -87,154 +274,29 @@ k_jfused(FusedArgs A)
 	// rows produced in the previous step, per stage (0..D) and the residual row (index D+1); 2 pad doubles per side
 	__shared__ __align__(16) double sh[2][D + 2][FJ_COLS + 4];
 	const LevelDev &F = A.F;
-	const int tid = threadIdx.x;
-	const int c0 = blockIdx.x * FJ_VALID;                 // first valid column of the tile
-	const int j0 = c0 - FJ_HALO + 2 * tid;                // this thread's columns j0, j0+1 (j0 even)
-	const int y0 = blockIdx.y * A.rows;
-	const int y1 = min(y0 + A.rows, F.ni);
-	const size_t P = (size_t)F.pitch;
-	const bool in0 = j0 >= 0 && j0 < F.nj, in1 = j0 + 1 >= 0 && j0 + 1 < F.nj;
-	const bool ld_ok = j0 >= 0 && j0 < F.pitch;           // the pair may be loaded (pad columns hold zeros)
-	const bool st_ok = j0 >= c0 && j0 < c0 + FJ_VALID && j0 < F.pitch;
-
-	Coef cu = load_coef(F, A.gni, F.i0);                  // uniform operator: one coefficient set
-	double2 win[D + 1][3];                                // win[s][k]: stage s, rows (newest-2+k); win[s][2] is the newest
-#pragma unroll
-	for (int s = 0; s <= D; ++s)
-#pragma unroll
-		for (int k = 0; k < 3; ++k) win[s][k] = make_double2(0.0, 0.0);
-	double2 bq[D + 1];                                    // bq[k] = b of row t-1-k
-#pragma unroll
-	for (int k = 0; k <= D; ++k) bq[k] = make_double2(0.0, 0.0);
-	double rw[3][3];                                      // POST_RESTRICT: residual rows (own .x, own .y, east) of rows rho'-2..rho'
-#pragma unroll
-	for (int k = 0; k < 3; ++k) { rw[k][0] = 0.0; rw[k][1] = 0.0; rw[k][2] = 0.0; }
-	double2 res_own = make_double2(0.0, 0.0);             // residual row produced in the previous step (own columns)
-	double acc = 0.0;
-
-	const int tb = y0 - D - 1, te = y1 + D + 2;
-	// software prefetch rings: rows t+FJ_PF of u and t-1+FJ_PF of b are requested FJ_PF steps ahead
-	double2 upf[FJ_PF], bpf[FJ_PF];
-	auto row_ok = [&](int i) { const int g = F.i0 + i; return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS; };
-	auto load_u = [&](int i) -> double2 {
-		if (PRE == PRE_ZERO || !ld_ok || !row_ok(i)) return make_double2(0.0, 0.0);
-		return ld2(A.u_in + (ptrdiff_t)i * (ptrdiff_t)P + j0);
-	};
-	auto load_b = [&](int i) -> double2 {
-		if (!ld_ok || !row_ok(i)) return make_double2(0.0, 0.0);
-		return ld2(A.b + (ptrdiff_t)i * (ptrdiff_t)P + j0);
-	};
-#pragma unroll
-	for (int k = 0; k < FJ_PF; ++k) { upf[k] = load_u(tb + k); bpf[k] = load_b(tb - 1 + k); }
-
-	for (int t = tb; t <= te; ++t) {
-		const int par = t & 1;
-		double (*shp)[FJ_COLS + 4] = sh[par ^ 1];        // rows of the previous step
-		double (*shn)[FJ_COLS + 4] = sh[par];            // rows of this step
-		// ---- A: stage 0 of row t, b of row t-1 (from the prefetch ring), next requests
-		double2 u0 = upf[0], bnew = bpf[0];
-#pragma unroll
-		for (int k = 0; k + 1 < FJ_PF; ++k) { upf[k] = upf[k + 1]; bpf[k] = bpf[k + 1]; }
-		upf[FJ_PF - 1] = load_u(t + FJ_PF);
-		bpf[FJ_PF - 1] = load_b(t - 1 + FJ_PF);
-#pragma unroll
-		for (int k = D; k > 0; --k) bq[k] = bq[k - 1];
-		bq[0] = bnew;
-		if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
-			if (ld_ok && row_ok(t)) {
-				u0 = prolonged<PRE == PRE_PROLONG_MULTADD>(u0, A.uc, t, j0, (size_t)A.C.pitch, A.P3);
-			}
-		}
-		if (!in0 || !row_ok(t)) u0.x = 0.0;
-		if (!in1 || !row_ok(t)) u0.y = 0.0;
-		win[0][0] = win[0][1]; win[0][1] = win[0][2]; win[0][2] = u0;
-		// ---- B: stage s of row t-s
-#pragma unroll
-		for (int s = 1; s <= D; ++s) {
-			const int c = t - s;                           // centre row
-			const int g = F.i0 + c;
-			Coef cf = cu;
-			if (!F.uniform) cf = load_coef(F, A.gni, g);
-			const double2 bb = bq[s - 1];                  // b of row t-s
-			double2 o;
-			if (PRE == PRE_ZERO && s == 1) {
-				// first Richardson iteration from a zero guess: r = b, x = 0 + scale * (r * dinv)
-				o.x = mul(A.scale, mul(bb.x, cf.dinv));
-				o.y = mul(A.scale, mul(bb.y, cf.dinv));
-			} else {
-				const double2 xm = win[s - 1][0], xc = win[s - 1][1], xn = win[s - 1][2];
-				const double2 wl = *reinterpret_cast<const double2 *>(&shp[s - 1][2 * tid]);       // columns j0-2, j0-1
-				const double2 er = *reinterpret_cast<const double2 *>(&shp[s - 1][2 * tid + 4]);   // columns j0+2, j0+3
-				const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, wl.y, xc.x, xc.y, xn.x);
-				const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, er.x, xn.y);
-				const double r0 = sub(bb.x, t0), r1 = sub(bb.y, t1);
-				o.x = add(xc.x, mul(A.scale, mul(r0, cf.dinv)));
-				o.y = add(xc.y, mul(A.scale, mul(r1, cf.dinv)));
-			}
-			const bool rok = g >= 0 && g < A.gni;
-			if (!in0 || !rok) o.x = 0.0;
-			if (!in1 || !rok) o.y = 0.0;
-			win[s][0] = win[s][1]; win[s][1] = win[s][2]; win[s][2] = o;
-		}
-		// ---- F: the finished row t-D
-		{
-			const int c = t - D;
-			if (st_ok && c >= y0 && c < y1) st2(A.u_out + (size_t)c * P + j0, win[D][2]);
-		}
-		// ---- C: residual of row rho = t-D-1 from stage D
-		double2 res = make_double2(0.0, 0.0);
-		if (POST != POST_NONE) {
-			const int rho = t - D - 1;
-			const int g = F.i0 + rho;
-			Coef cf = cu;
-			if (!F.uniform) cf = load_coef(F, A.gni, g);
-			const double2 xm = win[D][0], xc = win[D][1], xn = win[D][2];
-			const double2 wl = *reinterpret_cast<const double2 *>(&shp[D][2 * tid]);
-			const double2 er = *reinterpret_cast<const double2 *>(&shp[D][2 * tid + 4]);
-			const double2 bb = bq[D];
-			const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, wl.y, xc.x, xc.y, xn.x);
-			const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, er.x, xn.y);
-			res.x = sub(bb.x, t0); res.y = sub(bb.y, t1);
-			const bool rok = g >= 0 && g < A.gni;
-			if (!in0 || !rok) res.x = 0.0;
-			if (!in1 || !rok) res.y = 0.0;
-			if (POST == POST_NORM) {
-				if (st_ok && rho >= y0 && rho < y1) acc += res.x * res.x + res.y * res.y;
-			}
-		}
-		// ---- E: restriction of the residual rows completed in the previous step
-		if (POST == POST_RESTRICT) {
-			const int rp = t - D - 2;                      // residual row whose east neighbour is now visible
-			const double east = shp[D + 1][2 * tid + 4];   // column j0+2 of row rp
-			rw[0][0] = rw[1][0]; rw[0][1] = rw[1][1]; rw[0][2] = rw[1][2];
-			rw[1][0] = rw[2][0]; rw[1][1] = rw[2][1]; rw[1][2] = rw[2][2];
-			rw[2][0] = res_own.x; rw[2][1] = res_own.y; rw[2][2] = east;
-			if ((rp & 1) == 0) {
-				const int I = (rp >> 1) - 1;               // coarse row (local) fed by fine rows rp-2 .. rp
-				const int J = j0 >> 1;
-				if (st_ok && I >= (y0 >> 1) && I < (y1 >> 1) && I < A.C.ni && J < A.C.pitch) {
-					double sum = mul(A.R3.w[0], rw[0][0]);
-					sum = add(sum, mul(A.R3.w[1], rw[0][1]));
-					sum = add(sum, mul(A.R3.w[2], rw[0][2]));
-					sum = add(sum, mul(A.R3.w[3], rw[1][0]));
-					sum = add(sum, mul(A.R3.w[4], rw[1][1]));
-					sum = add(sum, mul(A.R3.w[5], rw[1][2]));
-					sum = add(sum, mul(A.R3.w[6], rw[2][0]));
-					sum = add(sum, mul(A.R3.w[7], rw[2][1]));
-					sum = add(sum, mul(A.R3.w[8], rw[2][2]));
-					A.bc[(size_t)I * A.C.pitch + J] = (J < A.C.nj) ? sum : 0.0;
-				}
-			}
-			res_own = res;
-		}
-		// ---- D: publish the rows produced in this step
-#pragma unroll
-		for (int s = 0; s <= D; ++s) *reinterpret_cast<double2 *>(&shn[s][2 * tid + 2]) = win[s][2];
-		if (POST != POST_NONE) *reinterpret_cast<double2 *>(&shn[D + 1][2 * tid + 2]) = res;
-		__syncthreads();
+	JfBlock B;
+	B.tid = threadIdx.x;
+	B.c0 = blockIdx.x * FJ_VALID;                         // first valid column of the tile
+	B.j0 = B.c0 - FJ_HALO + 2 * B.tid;                    // this thread's columns j0, j0+1 (j0 even)
+	B.y0 = blockIdx.y * A.rows;
+	B.y1 = min(B.y0 + A.rows, F.ni);
+	B.P = (ptrdiff_t)F.pitch;
+	B.in0 = B.j0 >= 0 && B.j0 < F.nj; B.in1 = B.j0 + 1 >= 0 && B.j0 + 1 < F.nj;
+	B.ld_ok = B.j0 >= 0 && B.j0 < F.pitch;                // the pair may be loaded (pad columns hold zeros)
+	B.st_ok = B.j0 >= B.c0 && B.j0 < B.c0 + FJ_VALID && B.j0 < F.pitch;
+	{
+		const Coef c = load_coef(F, A.gni, F.i0);         // uniform operator: one coefficient set
+		B.cu.aS = vreg(c.aS); B.cu.aW = vreg(c.aW); B.cu.aC = vreg(c.aC); B.cu.aE = vreg(c.aE); B.cu.aN = vreg(c.aN);
+		B.cu.dinv = vreg(c.dinv); B.scale = vreg(A.scale);
 	}
-	if (POST == POST_NORM) {
-		const double s = block_sum<FJ_THREADS>(acc);
-		if (tid == 0) A.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
-	}
+	// steps: stage 0 of row y0-D-1 is the first needed, the restriction of row y1 completes at step y1+D+2;
+	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
+	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 2;
+	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
+	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
+	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 6 < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) && (te + 6 < F.ni + MGB_GHOST_ROWS);
+	if (F.uniform) {
+		if (interior) jf_run<D, PRE, POST, false, true>(A, B, sh, tb, te);
+		else          jf_run<D, PRE, POST, true, true>(A, B, sh, tb, te);
+	} else            jf_run<D, PRE, POST, true, false>(A, B, sh, tb, te);
 }

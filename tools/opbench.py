@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--csr", type=int, default=0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--ops", default="", help="comma-separated subset of operations")
+    ap.add_argument("--maxlevel", type=int, default=99)
     a = ap.parse_args()
     n = a.npts - 2
     e = mgb.Engine(a.levels, n)
@@ -43,17 +45,21 @@ def main():
     rows = []
     print(f"# {a.npts}^2, {a.levels} levels, reps {a.reps}; HBM peak {peak} GB/s ({how})")
     print(f"{'level':>5} {'n':>6} {'op':>18} {'us':>10} {'GB/s':>9} {'frac':>6}")
-    for l in range(a.levels):
+    for l in range(min(a.levels, a.maxlevel + 1)):
         ni, nj = e.dims(l)
         for op, (code, bpu) in mgb.OPS.items():
             if op == "csr_spmv" and not a.csr:
                 continue
-            if op in ("residual_restrict", "prolong_correct") and l == a.levels - 1:
+            if op in ("residual_restrict", "prolong_correct", "fused_down", "fused_up", "fused_down_zero") and l == a.levels - 1:
+                continue
+            if a.ops and op not in a.ops.split(","):
                 continue
             ms = e.time_op(op, l, a.reps)
             gbs = bpu * ni * nj / (ms * 1e-3) / 1e9
-            rows.append({"level": l, "n": ni, "op": op, "us": ms * 1e3, "gbs": gbs, "frac": gbs / peak})
-            print(f"{l:5d} {ni:6d} {op:>18} {ms*1e3:10.2f} {gbs:9.1f} {gbs/peak:6.3f}")
+            own = mgb.FUSED_OWN_BYTES.get(op)
+            own_gbs = own * ni * nj / (ms * 1e-3) / 1e9 if own else None
+            rows.append({"level": l, "n": ni, "op": op, "us": ms * 1e3, "gbs": gbs, "frac": gbs / peak, "own_traffic_gbs": own_gbs})
+            print(f"{l:5d} {ni:6d} {op:>18} {ms*1e3:10.2f} {gbs:9.1f} {gbs/peak:6.3f}" + (f"   (own traffic {own_gbs:7.1f} GB/s)" if own else ""))
     if a.json:
         json.dump({"npts": a.npts, "levels": a.levels, "peak_gbs": peak, "peak_kind": how, "rows": rows}, open(a.json, "w"), indent=1)
     e.close()

@@ -1054,7 +1054,12 @@ static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 #define HALO_DEPTH MGB_GHOST_ROWS
 
 template <int D, int PRE, int POST>
-static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st) { k_jfused<D, PRE, POST><<<grid, FJ_THREADS, 0, st>>>(a); }
+static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st)
+{
+	static bool optin = false;                 // > 48 KB of dynamic shared memory needs the opt-in once per kernel
+	if (!optin) { cudaFuncSetAttribute(k_jfused<D, PRE, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jf_smem_bytes<D>()); optin = true; }
+	k_jfused<D, PRE, POST><<<grid, FJ_THREADS, jf_smem_bytes<D>(), st>>>(a);
+}
 
 template <int D>
 static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cudaStream_t st)

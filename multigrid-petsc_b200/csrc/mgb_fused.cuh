@@ -34,6 +34,19 @@
 #define FJ_HALO 6
 #define FJ_VALID (FJ_COLS - 2 * FJ_HALO)
 #define FJ_MAXD 3
+#define FJ_NR 8                                   // rows of the cp.async input rings (u and b)
+#define FJ_PF 6                                   // rows requested ahead of their use
+#define FJ_PUB (FJ_COLS + 4)                      // doubles per published row (2 pad doubles per side)
+template <int D> constexpr size_t jf_smem_bytes() { return sizeof(double) * ((size_t)2 * (D + 2) * FJ_PUB + (size_t)2 * FJ_NR * FJ_COLS); }
+
+// 16-byte asynchronous copy global -> shared (LDGSTS), bypassing L1: the input rows are consumed exactly once
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 enum { PRE_GIVEN = 0, PRE_ZERO = 1, PRE_PROLONG = 2, PRE_PROLONG_MULTADD = 3 };
 enum { POST_NONE = 0, POST_RESTRICT = 1, POST_NORM = 2 };
@@ -91,7 +104,6 @@ struct JfState {
 	double2 win[D + 1][4];   // win[s][row & 3]: stage s of that row (rows t-s-2 .. t-s live)
 	double2 bq[4];           // b of rows t-4 .. t-1
 	double rw[4][3];         // POST_RESTRICT: residual row (own .x, own .y, east neighbour)
-	double2 upf[2], bpf[2];  // requested rows: u of rows t, t+1 ; b of rows t-1, t
 	double acc;
 };
 
@@ -109,28 +121,47 @@ struct JfBlock {
 __device__ __forceinline__ double vreg(double x) { double y; asm volatile("mov.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
 
 // one row step; K = t & 3 (compile time), MASK = the block touches the outside of the grid
+// request rows `i` of u and b into the input rings (one commit group per call, possibly empty)
+template <int PRE, bool MASK>
+__device__ __forceinline__ void jf_request(const FusedArgs &A, const JfBlock &B, double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int i)
+{
+	const LevelDev &F = A.F;
+	const int slot = i & (FJ_NR - 1);
+	bool ok = true;
+	if (MASK) {
+		const int g = F.i0 + i;
+		ok = B.ld_ok && g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
+	}
+	if (ok) {
+		if (PRE != PRE_ZERO) cp_async16(&in_u[slot][2 * B.tid], A.u_in + (ptrdiff_t)i * B.P + B.j0);
+		cp_async16(&in_b[slot][2 * B.tid], A.b + (ptrdiff_t)i * B.P + B.j0);
+	} else {
+		if (PRE != PRE_ZERO) *reinterpret_cast<double2 *>(&in_u[slot][2 * B.tid]) = make_double2(0.0, 0.0);
+		*reinterpret_cast<double2 *>(&in_b[slot][2 * B.tid]) = make_double2(0.0, 0.0);
+	}
+	cp_async_commit();
+}
+
 template <int D, int PRE, int POST, bool MASK, bool UNI, int K>
-__device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, JfState<D> &S, double (*sh)[D + 2][FJ_COLS + 4], int t)
+__device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, JfState<D> &S, double (*sh)[D + 2][FJ_PUB],
+                                        double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int t)
 {
 	const LevelDev &F = A.F;
 	constexpr int par = K & 1;
-	double (*shp)[FJ_COLS + 4] = sh[par ^ 1];            // rows published in the previous step
-	double (*shn)[FJ_COLS + 4] = sh[par];
+	double (*shp)[FJ_PUB] = sh[par ^ 1];                 // rows published in the previous step
+	double (*shn)[FJ_PUB] = sh[par];
 	const int tid = B.tid;
 	auto row_ok = [&](int i) {
 		if (!MASK) return true;
 		const int g = F.i0 + i;
 		return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
 	};
-	// ---- stage 0 of row t and b of row t-1 arrive; rows t+2 / t+1 are requested
-	double2 u0 = S.upf[K & 1];
-	S.bq[(K + 3) & 3] = S.bpf[K & 1];                     // slot of row t-1
-	if (PRE != PRE_ZERO) {
-		if (!MASK || (B.ld_ok && row_ok(t + 2))) S.upf[K & 1] = ld2(A.u_in + (ptrdiff_t)(t + 2) * B.P + B.j0);
-		else S.upf[K & 1] = make_double2(0.0, 0.0);
-	}
-	if (!MASK || (B.ld_ok && row_ok(t + 1))) S.bpf[K & 1] = ld2(A.b + (ptrdiff_t)(t + 1) * B.P + B.j0);
-	else S.bpf[K & 1] = make_double2(0.0, 0.0);
+	// ---- rows t+FJ_PF are requested; stage 0 of row t and b of row t-1 have arrived in the input rings
+	jf_request<PRE, MASK>(A, B, in_u, in_b, t + FJ_PF);
+	cp_async_wait<FJ_PF>();
+	double2 u0 = make_double2(0.0, 0.0);
+	if (PRE != PRE_ZERO) u0 = *reinterpret_cast<const double2 *>(&in_u[t & (FJ_NR - 1)][2 * tid]);
+	S.bq[(K + 3) & 3] = *reinterpret_cast<const double2 *>(&in_b[(t - 1) & (FJ_NR - 1)][2 * tid]);   // slot of row t-1
 	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
 		if (!MASK || (B.ld_ok && row_ok(t)))
 			u0 = prolonged<PRE == PRE_PROLONG_MULTADD>(u0, A.uc, t, B.j0, (ptrdiff_t)A.C.pitch, A.P3);
@@ -232,7 +263,8 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 }
 
 template <int D, int PRE, int POST, bool MASK, bool UNI>
-__device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, double (*sh)[D + 2][FJ_COLS + 4], int t0, int t1)
+__device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, double (*sh)[D + 2][FJ_PUB],
+                                       double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int t0, int t1)
 {
 	JfState<D> S;
 #pragma unroll
@@ -248,18 +280,13 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 		const int g = F.i0 + i;
 		return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
 	};
-	// requests for the first two steps (t0 is a multiple of 4: slots 0, 1)
-#pragma unroll
-	for (int k = 0; k < 2; ++k) {
-		S.upf[k] = (PRE != PRE_ZERO && (!MASK || (B.ld_ok && row_ok(t0 + k)))) ? ld2(A.u_in + (ptrdiff_t)(t0 + k) * B.P + B.j0) : make_double2(0.0, 0.0);
-		// bpf[k & 1] at step t holds b of row t-1: steps t0, t0+1 consume rows t0-1, t0
-		S.bpf[k] = (!MASK || (B.ld_ok && row_ok(t0 - 1 + k))) ? ld2(A.b + (ptrdiff_t)(t0 - 1 + k) * B.P + B.j0) : make_double2(0.0, 0.0);
-	}
+	// rows t0-1 .. t0+FJ_PF-1 are requested up front, one commit group each (row t0-1 only feeds the b ring)
+	for (int i = t0 - 1; i < t0 + FJ_PF; ++i) jf_request<PRE, MASK>(A, B, in_u, in_b, i);
 	for (int t = t0; t <= t1; t += 4) {
-		jf_step<D, PRE, POST, MASK, UNI, 0>(A, B, S, sh, t);
-		jf_step<D, PRE, POST, MASK, UNI, 1>(A, B, S, sh, t + 1);
-		jf_step<D, PRE, POST, MASK, UNI, 2>(A, B, S, sh, t + 2);
-		jf_step<D, PRE, POST, MASK, UNI, 3>(A, B, S, sh, t + 3);
+		jf_step<D, PRE, POST, MASK, UNI, 0>(A, B, S, sh, in_u, in_b, t);
+		jf_step<D, PRE, POST, MASK, UNI, 1>(A, B, S, sh, in_u, in_b, t + 1);
+		jf_step<D, PRE, POST, MASK, UNI, 2>(A, B, S, sh, in_u, in_b, t + 2);
+		jf_step<D, PRE, POST, MASK, UNI, 3>(A, B, S, sh, in_u, in_b, t + 3);
 	}
 	if (POST == POST_NORM) {
 		const double s = block_sum<FJ_THREADS>(S.acc);
@@ -271,8 +298,12 @@ template <int D, int PRE, int POST>
 __global__ void __launch_bounds__(FJ_THREADS)
 k_jfused(FusedArgs A)
 {
-	// rows produced in the previous step, per stage (0..D) and the residual row (index D+1); 2 pad doubles per side
-	__shared__ __align__(16) double sh[2][D + 2][FJ_COLS + 4];
+	// dynamic shared memory: rows produced in the previous step, per stage (0..D) and the residual row (index D+1),
+	// double-buffered; then the cp.async input rings of u and b (FJ_NR rows each)
+	extern __shared__ __align__(16) unsigned char jf_smem[];
+	double (*sh)[D + 2][FJ_PUB] = reinterpret_cast<double (*)[D + 2][FJ_PUB]>(jf_smem);
+	double (*in_u)[FJ_COLS] = reinterpret_cast<double (*)[FJ_COLS]>(jf_smem + sizeof(double) * 2 * (D + 2) * FJ_PUB);
+	double (*in_b)[FJ_COLS] = in_u + FJ_NR;
 	const LevelDev &F = A.F;
 	JfBlock B;
 	B.tid = threadIdx.x;
@@ -294,9 +325,10 @@ k_jfused(FusedArgs A)
 	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 2;
 	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
 	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
-	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 6 < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) && (te + 6 < F.ni + MGB_GHOST_ROWS);
+	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 4 + FJ_PF < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) &&
+	                      (te + 4 + FJ_PF < F.ni + MGB_GHOST_ROWS);
 	if (F.uniform) {
-		if (interior) jf_run<D, PRE, POST, false, true>(A, B, sh, tb, te);
-		else          jf_run<D, PRE, POST, true, true>(A, B, sh, tb, te);
-	} else            jf_run<D, PRE, POST, true, false>(A, B, sh, tb, te);
+		if (interior) jf_run<D, PRE, POST, false, true>(A, B, sh, in_u, in_b, tb, te);
+		else          jf_run<D, PRE, POST, true, true>(A, B, sh, in_u, in_b, tb, te);
+	} else            jf_run<D, PRE, POST, true, false>(A, B, sh, in_u, in_b, tb, te);
 }

@@ -74,27 +74,27 @@ __device__ __forceinline__ Coef load_coef(const LevelDev &L, int gni, int grow)
 	return c;
 }
 
-// u + pro * uc at fine row i (local), columns j0, j0+1 -- the arithmetic of k_prolong_add, natural numbering
+// u + pro * uc at fine columns j0, j0+1 -- the arithmetic of k_prolong_add, natural numbering.
+// odd fine row: cm / c0 = coarse row (i-1)/2, columns J0-1 / J0.  even fine row: (am, a0) = coarse row i/2-1, (bm, b0) = row i/2.
 template <int MULTADD>
-__device__ __forceinline__ double2 prolonged(double2 u, const double *__restrict__ uc, int i, int j0, ptrdiff_t PC, const Stencil3 &Pw)
+__device__ __forceinline__ double2 prolonged_odd(double2 u, double cmv, double c0v, const Stencil3 &Pw)
 {
-	const int J0 = j0 >> 1, Jm = J0 - 1;
+	const double cm = mul(Pw.w[3 + 2], cmv), c0 = mul(Pw.w[3 + 0], c0v);
+	const double s0 = mul(Pw.w[3 + 1], c0v);
 	double e0, e1;
-	if (i & 1) {
-		const double *c = uc + (ptrdiff_t)((i - 1) >> 1) * PC;
-		const double cm = mul(Pw.w[3 + 2], c[Jm]), c0 = mul(Pw.w[3 + 0], c[J0]);
-		const double s0 = mul(Pw.w[3 + 1], c[J0]);
-		if (MULTADD) { e0 = add(add(u.x, cm), c0); e1 = add(u.y, s0); }
-		else { e0 = add(u.x, mul(1.0, add(cm, c0))); e1 = add(u.y, mul(1.0, s0)); }
-	} else {
-		const double *cA = uc + (ptrdiff_t)((i >> 1) - 1) * PC;
-		const double *cB = cA + PC;
-		const double am = mul(Pw.w[6 + 2], cA[Jm]), a0 = mul(Pw.w[6 + 0], cA[J0]);
-		const double bm = mul(Pw.w[0 + 2], cB[Jm]), b0 = mul(Pw.w[0 + 0], cB[J0]);
-		const double sa = mul(Pw.w[6 + 1], cA[J0]), sb = mul(Pw.w[0 + 1], cB[J0]);
-		if (MULTADD) { e0 = add(add(add(add(u.x, am), a0), bm), b0); e1 = add(add(u.y, sa), sb); }
-		else { e0 = add(u.x, mul(1.0, add(add(add(am, a0), bm), b0))); e1 = add(u.y, mul(1.0, add(sa, sb))); }
-	}
+	if (MULTADD) { e0 = add(add(u.x, cm), c0); e1 = add(u.y, s0); }
+	else { e0 = add(u.x, mul(1.0, add(cm, c0))); e1 = add(u.y, mul(1.0, s0)); }
+	return make_double2(e0, e1);
+}
+template <int MULTADD>
+__device__ __forceinline__ double2 prolonged_even(double2 u, double amv, double a0v, double bmv, double b0v, const Stencil3 &Pw)
+{
+	const double am = mul(Pw.w[6 + 2], amv), a0 = mul(Pw.w[6 + 0], a0v);
+	const double bm = mul(Pw.w[0 + 2], bmv), b0 = mul(Pw.w[0 + 0], b0v);
+	const double sa = mul(Pw.w[6 + 1], a0v), sb = mul(Pw.w[0 + 1], b0v);
+	double e0, e1;
+	if (MULTADD) { e0 = add(add(add(add(u.x, am), a0), bm), b0); e1 = add(add(u.y, sa), sb); }
+	else { e0 = add(u.x, mul(1.0, add(add(add(am, a0), bm), b0))); e1 = add(u.y, mul(1.0, add(sa, sb))); }
 	return make_double2(e0, e1);
 }
 
@@ -104,6 +104,8 @@ struct JfState {
 	double2 win[D + 1][4];   // win[s][row & 3]: stage s of that row (rows t-s-2 .. t-s live)
 	double2 bq[4];           // b of rows t-4 .. t-1
 	double rw[4][3];         // POST_RESTRICT: residual row (own .x, own .y, east neighbour)
+	double2 cq[3];           // PRE_PROLONG*: coarse rows T-1, T, T+1 (columns J0-1, J0) of the current group of four fine rows
+	double2 cn[2];           //               coarse rows T+2, T+3 requested for the next group
 	double acc;
 };
 
@@ -163,8 +165,11 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	if (PRE != PRE_ZERO) u0 = *reinterpret_cast<const double2 *>(&in_u[t & (FJ_NR - 1)][2 * tid]);
 	S.bq[(K + 3) & 3] = *reinterpret_cast<const double2 *>(&in_b[(t - 1) & (FJ_NR - 1)][2 * tid]);   // slot of row t-1
 	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
-		if (!MASK || (B.ld_ok && row_ok(t)))
-			u0 = prolonged<PRE == PRE_PROLONG_MULTADD>(u0, A.uc, t, B.j0, (ptrdiff_t)A.C.pitch, A.P3);
+		// t = 4m + K: coarse rows T-1, T, T+1 with T = 2m are in cq[0..2] (fine rows t..t+3 of the group need exactly these)
+		if (K == 0) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[0].x, S.cq[0].y, S.cq[1].x, S.cq[1].y, A.P3);
+		if (K == 1) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[1].x, S.cq[1].y, A.P3);
+		if (K == 2) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[1].x, S.cq[1].y, S.cq[2].x, S.cq[2].y, A.P3);
+		if (K == 3) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[2].x, S.cq[2].y, A.P3);
 	}
 	if (MASK) {
 		const bool rk = row_ok(t);
@@ -282,11 +287,29 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 	};
 	// rows t0-1 .. t0+FJ_PF-1 are requested up front, one commit group each (row t0-1 only feeds the b ring)
 	for (int i = t0 - 1; i < t0 + FJ_PF; ++i) jf_request<PRE, MASK>(A, B, in_u, in_b, i);
+	// coarse values of one coarse row (columns J0-1, J0); rows outside the coarse arrays are clamped (their fine rows are masked)
+	auto load_c = [&](int I) -> double2 {
+		if (MASK) {
+			if (!B.ld_ok) return make_double2(0.0, 0.0);
+			I = I < -MGB_GHOST_ROWS ? -MGB_GHOST_ROWS : (I > A.C.ni + MGB_GHOST_ROWS - 1 ? A.C.ni + MGB_GHOST_ROWS - 1 : I);
+		}
+		const double *c = A.uc + (ptrdiff_t)I * (ptrdiff_t)A.C.pitch + (B.j0 >> 1);
+		return make_double2(c[-1], c[0]);
+	};
+	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
+		const int T = t0 >> 1;
+		S.cq[0] = load_c(T - 1); S.cq[1] = load_c(T); S.cq[2] = load_c(T + 1);
+	}
 	for (int t = t0; t <= t1; t += 4) {
+		if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
+			const int T = (t >> 1) + 2;                    // the next group of four fine rows needs coarse rows T-1 (held), T, T+1
+			S.cn[0] = load_c(T); S.cn[1] = load_c(T + 1);
+		}
 		jf_step<D, PRE, POST, MASK, UNI, 0>(A, B, S, sh, in_u, in_b, t);
 		jf_step<D, PRE, POST, MASK, UNI, 1>(A, B, S, sh, in_u, in_b, t + 1);
 		jf_step<D, PRE, POST, MASK, UNI, 2>(A, B, S, sh, in_u, in_b, t + 2);
 		jf_step<D, PRE, POST, MASK, UNI, 3>(A, B, S, sh, in_u, in_b, t + 3);
+		if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) { S.cq[0] = S.cq[2]; S.cq[1] = S.cn[0]; S.cq[2] = S.cn[1]; }
 	}
 	if (POST == POST_NORM) {
 		const double s = block_sum<FJ_THREADS>(S.acc);

@@ -36,7 +36,10 @@
 #define FJ_MAXD 3
 #define FJ_NR 8                                   // rows of the cp.async input rings (u and b)
 #define FJ_PF 6                                   // rows requested ahead of their use
-#define FJ_PUB (FJ_COLS + 4)                      // doubles per published row (2 pad doubles per side)
+#define FJ_PUB (FJ_COLS + 8)                      // doubles per published row: X[-1..128] then Y[-1..128] (split so that
+                                                  // neighbour reads are conflict-free 8-byte accesses)
+#define FJ_X(tid) ((tid) + 1)                     // left column (j0) of thread tid
+#define FJ_Y(tid) ((tid) + 1 + FJ_THREADS + 4)    // right column (j0+1) of thread tid
 template <int D> constexpr size_t jf_smem_bytes() { return sizeof(double) * ((size_t)2 * (D + 2) * FJ_PUB + (size_t)2 * FJ_NR * FJ_COLS); }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS), bypassing L1: the input rows are consumed exactly once
@@ -193,8 +196,8 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 			o.y = mul(B.scale, mul(bb.y, cf.dinv));
 		} else {
 			const double2 xm = S.win[s - 1][(K - s - 1) & 3], xc = S.win[s - 1][(K - s) & 3], xn = S.win[s - 1][(K - s + 1) & 3];
-			const double xw = shp[s - 1][2 * tid + 1];    // column j0-1
-			const double xe = shp[s - 1][2 * tid + 4];    // column j0+2
+			const double xw = shp[s - 1][FJ_Y(tid - 1)];  // column j0-1
+			const double xe = shp[s - 1][FJ_X(tid + 1)];  // column j0+2
 			const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, xw, xc.x, xc.y, xn.x);
 			const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, xe, xn.y);
 			const double r0 = sub(bb.x, t0), r1 = sub(bb.y, t1);
@@ -221,8 +224,8 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 		Coef cf = B.cu;
 		if (!UNI) cf = load_coef(F, A.gni, g);
 		const double2 xm = S.win[D][(K - D - 2) & 3], xc = S.win[D][(K - D - 1) & 3], xn = S.win[D][(K - D) & 3];
-		const double xw = shp[D][2 * tid + 1];
-		const double xe = shp[D][2 * tid + 4];
+		const double xw = shp[D][FJ_Y(tid - 1)];
+		const double xe = shp[D][FJ_X(tid + 1)];
 		const double2 bb = S.bq[(K - D - 1) & 3];
 		const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, xw, xc.x, xc.y, xn.x);
 		const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, xe, xn.y);
@@ -239,7 +242,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	// ---- restriction of the residual rows completed in the previous step (their east neighbours are visible now)
 	if (POST == POST_RESTRICT) {
 		constexpr int RP = (K - D - 2) & 3;               // slot of row rp = t-D-2
-		S.rw[RP][2] = shp[D + 1][2 * tid + 4];            // column j0+2 of row rp
+		S.rw[RP][2] = shp[D + 1][FJ_X(tid + 1)];          // column j0+2 of row rp
 		if ((((K - D - 2) & 1) == 0)) {
 			const int rp = t - D - 2;
 			const int I = (rp >> 1) - 1;                   // coarse row (local) fed by fine rows rp-2 .. rp
@@ -262,8 +265,8 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	}
 	// ---- publish the rows produced in this step
 #pragma unroll
-	for (int s = 0; s <= D; ++s) *reinterpret_cast<double2 *>(&shn[s][2 * tid + 2]) = S.win[s][(K - s) & 3];
-	if (POST != POST_NONE) *reinterpret_cast<double2 *>(&shn[D + 1][2 * tid + 2]) = res;
+	for (int s = 0; s <= D; ++s) { shn[s][FJ_X(tid)] = S.win[s][(K - s) & 3].x; shn[s][FJ_Y(tid)] = S.win[s][(K - s) & 3].y; }
+	if (POST == POST_RESTRICT) shn[D + 1][FJ_X(tid)] = res.x;     // only the east neighbour's left column is ever read
 	__syncthreads();
 }
 

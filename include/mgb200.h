@@ -163,6 +163,8 @@ typedef struct {
 	int    use_graph;       /* 1: replay the cycle as a CUDA graph (same kernels, same order)    */
 	int    no_fuse;         /* 1: one kernel per sweep / transfer (default 0: each leg of a level in one pass,
 	                           csrc/mgb_fused.cuh -- same arithmetic per value, bit-identical results)          */
+	int    no_bottom;       /* 1: do not run the levels with <= 255 rows as one persistent cluster launch
+	                           (csrc/mgb_coarse_cycle.cuh); only meaningful with the fused legs                 */
 } mgb_vcycle_params;
 
 /* rnorm: max_iter+1 doubles; on return rnorm[0..num_iter] are the RELATIVE residual norms
@@ -180,7 +182,7 @@ typedef struct {
 	mgb_smoother level_smoother; int level_its;     /* -mg_levels_*                               */
 	int    coarse;           /* MGB_COARSE_*                                                      */
 	mgb_smoother coarse_smoother; int coarse_its;   /* -mg_coarse_*                               */
-	int    no_fuse;          /* as in mgb_vcycle_params                                            */
+	int    no_fuse, no_bottom; /* as in mgb_vcycle_params                                          */
 } mgb_pcmg_params;
 /* reason: >0 converged (2 = rtol, 3 = atol, 4 = its), <0 diverged (PETSc KSPConvergedReason values) */
 int  mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *rnorm, int *num_iter, int *reason, double *seconds);
@@ -195,7 +197,8 @@ double mgb_last_solve_ms(const mgb_engine *e);
  * op: 0 apply, 1 residual, 2 jacobi sweep, 3 red-black full sweep (2 half sweeps), 4 fused residual+restrict,
  * 5 prolong+correct, 6 residual norm, 7 csr spmv (A), 8 nrm2, 9 dot, 10 axpy; fused legs (mgb_fused.cuh):
  * 11 down leg (3 sweeps + residual + restriction), 12 up leg (prolongation + 3 sweeps + residual norm),
- * 13 three sweeps, 14 one sweep, 15 down leg from a zero guess.  ms_per_launch is the average. */
+ * 13 three sweeps, 14 one sweep, 15 down leg from a zero guess; 16 the persistent bottom kernel from `level`
+ * down to the coarsest and back (mgb_coarse_cycle.cuh).  ms_per_launch is the average. */
 int  mgb_time_op(mgb_engine *e, int op, int level, int reps, double *ms_per_launch);
 
 #ifdef __cplusplus

@@ -36,7 +36,7 @@ OPS = {"apply": (0, 16), "residual": (1, 24), "jacobi": (2, 24), "rbsor_full": (
        # fused legs: bytes of the UNFUSED sequence they replace (3 x 24 + 18, 18 + 3 x 24 + 16, 3 x 24, 24, 16 + 2 x 24 + 18)
        # and, second number, their own compulsory traffic (read u, b; write u; +2 coarse)
        "fused_down": (11, 90), "fused_up": (12, 106), "fused_3sweeps": (13, 72), "fused_1sweep": (14, 24),
-       "fused_down_zero": (15, 82)}
+       "fused_down_zero": (15, 82), "bottom_cycle": (16, 176)}
 FUSED_OWN_BYTES = {"fused_down": 26, "fused_up": 26, "fused_3sweeps": 24, "fused_1sweep": 24, "fused_down_zero": 18}
 
 
@@ -68,13 +68,13 @@ class Config(C.Structure):
 
 class VcycleParams(C.Structure):
     _fields_ = [("smoother", Smoother), ("v0", C.c_int), ("v1", C.c_int), ("max_iter", C.c_int),
-                ("rtol", C.c_double), ("use_graph", C.c_int), ("no_fuse", C.c_int)]
+                ("rtol", C.c_double), ("use_graph", C.c_int), ("no_fuse", C.c_int), ("no_bottom", C.c_int)]
 
 
 class PcmgParams(C.Structure):
     _fields_ = [("outer", C.c_int), ("rtol", C.c_double), ("abstol", C.c_double), ("dtol", C.c_double),
                 ("max_iter", C.c_int), ("level_smoother", Smoother), ("level_its", C.c_int), ("coarse", C.c_int),
-                ("coarse_smoother", Smoother), ("coarse_its", C.c_int), ("no_fuse", C.c_int)]
+                ("coarse_smoother", Smoother), ("coarse_its", C.c_int), ("no_fuse", C.c_int), ("no_bottom", C.c_int)]
 
 
 class RunResult(C.Structure):
@@ -307,17 +307,17 @@ class Engine:
         self._ck(self.L.mgb_op_aypx(self.h, yw, C.c_double(beta), xw, l))
 
     # solvers
-    def solve_vcycle(self, smoother, v0=3, v1=3, max_iter=100, rtol=1e-7, use_graph=True, fuse=True):
-        p = VcycleParams(smoother, v0, v1, max_iter, rtol, int(use_graph), int(not fuse))
+    def solve_vcycle(self, smoother, v0=3, v1=3, max_iter=100, rtol=1e-7, use_graph=True, fuse=True, bottom=True):
+        p = VcycleParams(smoother, v0, v1, max_iter, rtol, int(use_graph), int(not fuse), int(not bottom))
         rn = np.zeros(max_iter + 1)
         it, sec = C.c_int(), C.c_double()
         self._ck(self.L.mgb_solve_vcycle(self.h, C.byref(p), _pd(rn), C.byref(it), C.byref(sec)))
         return it.value, rn[: it.value + 1].copy(), sec.value
 
     def solve_pcmg(self, outer, level_smoother, level_its, coarse=COARSE_LU, coarse_smoother=None, coarse_its=1,
-                   rtol=1e-7, abstol=1e-50, dtol=1e4, max_iter=100, fuse=True):
+                   rtol=1e-7, abstol=1e-50, dtol=1e4, max_iter=100, fuse=True, bottom=True):
         cs = coarse_smoother if coarse_smoother is not None else jacobi(1.0)
-        p = PcmgParams(outer, rtol, abstol, dtol, max_iter, level_smoother, level_its, coarse, cs, coarse_its, int(not fuse))
+        p = PcmgParams(outer, rtol, abstol, dtol, max_iter, level_smoother, level_its, coarse, cs, coarse_its, int(not fuse), int(not bottom))
         rn = np.zeros(max_iter + 1)
         it, reason, sec = C.c_int(), C.c_int(), C.c_double()
         self._ck(self.L.mgb_solve_pcmg(self.h, C.byref(p), _pd(rn), C.byref(it), C.byref(reason), C.byref(sec)))

@@ -28,6 +28,7 @@
 #include "mgb_coarse.cuh"
 #include "mgb_halo.cuh"
 #include "mgb_fused.cuh"
+#include "mgb_coarse_cycle.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -126,6 +127,7 @@ struct mgb_engine {
 	bool csr_built = false;
 	cudaGraphExec_t gexec[2] = {nullptr, nullptr};
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
+	int coarse_threshold = 255;              // levels with at most this many rows run in the persistent bottom kernel
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
 
@@ -1144,6 +1146,45 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 	return MGB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent bottom of the cycle
+// first level handled by k_coarse_cycle: the finest level l >= 1 that is whole on rank 0 and has at most
+// coarse_threshold rows (L if there is none or the bottom has too many levels for one launch)
+static int bottom_start(const mgb_engine *e)
+{
+	if (e->coarse_threshold <= 0) return e->L;
+	for (int l = 1; l < e->L; ++l)
+		if (!e->geo[l].dist && e->geo[l].gni <= e->coarse_threshold && e->geo[l].nj <= 2 * e->coarse_threshold)
+			return (e->L - l <= CC_MAXLEV) ? l : e->L;
+	return e->L;
+}
+// levels lp .. L-1 in one launch on rank 0: zero-guess smoothing and restriction down, the coarsest smoothing,
+// correction and smoothing up.  b[lp] must be complete on rank 0; on return u[lp] holds the correction.
+static int bottom_cycle(mgb_engine *e, int lp, int its_level, double scale_level, int its_coarse, double scale_coarse, bool multadd)
+{
+	for (auto &s : e->strips) {
+		if (s.rank != 0) continue;
+		CoarseArgs a; memset(&a, 0, sizeof a);
+		a.nlev = e->L - lp; a.multadd = multadd ? 1 : 0; a.R3 = e->R3; a.P3 = e->P3;
+		for (int l = lp; l < e->L; ++l) {
+			SLevel &S = s.lev[l]; CLevel &c = a.lev[l - lp];
+			const bool last = l == e->L - 1;
+			c.x = S.v[MGB_VEC_U]; c.w = S.v[MGB_VEC_W]; c.b = S.v[MGB_VEC_B]; c.coef = S.coef;
+			c.ni = S.ni; c.nj = e->geo[l].nj; c.pitch = e->geo[l].pitch; c.uniform = e->geo[l].uniform;
+			c.its_down = last ? its_coarse : its_level; c.its_up = last ? 0 : its_level;
+			c.scale = last ? scale_coarse : scale_level;
+		}
+		k_coarse_cycle<<<CC_CTAS, CC_THREADS, 0, s.stream>>>(a);
+		LAUNCHED(e); KCHECK();
+	}
+	for (int l = lp; l < e->L; ++l) {
+		const bool last = l == e->L - 1;
+		const int swaps = last ? its_coarse - 1 : (its_level - 1) + its_level;
+		if (swaps & 1) swap_vec(e, l, MGB_VEC_U, MGB_VEC_W);
+	}
+	return MGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ single ops (C-ABI)
 // The single operations are collective in a multi-rank run.  They refresh the ghost rows of their inputs first
 // (vectors may have been set from the host); the solvers keep ghosts valid incrementally.
@@ -1293,11 +1334,13 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 		if (Lc == 1) {
 			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_NORM, B, U, W, 0));
 		} else {
+			const int lp = p->no_bottom ? Lc : bottom_start(e);   // levels lp .. Lc-1: one persistent launch
 			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));      // :1531-1535
-			for (int l = 1; l < Lc - 1; ++l)
+			for (int l = 1; l < Lc - 1 && l < lp; ++l)
 				TRY(fused_leg(e, l, s, p->v0, PRE_ZERO, POST_RESTRICT, B, U, W, 0));                     // :1534-1536
-			TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0));                         // :1536 coarsest
-			for (int l = Lc - 2; l >= 0; --l) {
+			if (lp < Lc) TRY(bottom_cycle(e, lp, p->v0, s->scale, p->v1, s->scale, false));
+			else TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0));                    // :1536 coarsest
+			for (int l = (lp < Lc ? lp - 1 : Lc - 2); l >= 0; --l) {
 				if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(bcast_rows(e, l + 1, U));
 				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0));  // :1540-1546
 			}
@@ -1412,6 +1455,10 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, int xv)
 {
 	const int Lc = e->L;
+	if (l >= 1 && !p->no_fuse && !p->no_bottom && p->coarse == MGB_COARSE_RICHARDSON && fusable(e, &p->level_smoother) &&
+	    fusable(e, &p->coarse_smoother) && p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e) &&
+	    bv == MGB_VEC_B && xv == MGB_VEC_U)
+		return bottom_cycle(e, l, p->level_its, p->level_smoother.scale, p->coarse_its, p->coarse_smoother.scale, true);
 	if (l == Lc - 1) {
 		if (p->coarse == MGB_COARSE_RICHARDSON) {
 			if (!p->no_fuse && fusable(e, &p->coarse_smoother) && p->coarse_its >= 1)
@@ -1592,6 +1639,8 @@ extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *m
 			case 13: TRY(fused_leg(e, level, &jac, 3, PRE_GIVEN, POST_NONE, B, U, MGB_VEC_W, 0)); break;
 			case 14: TRY(fused_leg(e, level, &jac, 1, PRE_GIVEN, POST_NONE, B, U, MGB_VEC_W, 0)); break;
 			case 15: TRY(fused_leg(e, level, &jac, 3, PRE_ZERO, POST_RESTRICT, B, U, MGB_VEC_W, 0)); break;
+			case 16: if (level < 1) return fail(MGB_EINVAL, "the bottom kernel starts at level >= 1");
+			         TRY(bottom_cycle(e, level, 3, 0.8, 3, 0.8, false)); break;
 			default: return fail(MGB_EINVAL, "unknown op %d", op);
 			}
 		}

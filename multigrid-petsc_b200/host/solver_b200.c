@@ -228,7 +228,7 @@ static void solve_vcycle(Solver *solver)
 	pbopt_get_real("-rtol", &p.rtol);
 	p.use_graph = 1;
 	pbopt_get_int("-mgb_graph", &p.use_graph);
-	{ int fuse = 1; pbopt_get_int("-mgb_fuse", &fuse); p.no_fuse = !fuse; }
+	{ int fuse = 1, bottom = 1; pbopt_get_int("-mgb_fuse", &fuse); pbopt_get_int("-mgb_bottom", &bottom); p.no_fuse = !fuse; p.no_bottom = !bottom; }
 	int iters = 0; double seconds = 0.0;
 	const clock_t c0 = clock();
 	if (mgb_solve_vcycle(e, &p, solver->rnorm, &iters, &seconds) != MGB_OK) die("mgb_solve_vcycle");
@@ -275,7 +275,7 @@ static void solve_pcmg(Solver *solver)
 		if (p.coarse_smoother.type < 0) refuse("-mg_coarse_ksp_type richardson needs -mg_coarse_pc_type jacobi|sor");
 	} else refuse("cycle 8: coarse solver must be preonly+lu (default) or richardson+jacobi|sor");
 
-	{ int fuse = 1; pbopt_get_int("-mgb_fuse", &fuse); p.no_fuse = !fuse; }
+	{ int fuse = 1, bottom = 1; pbopt_get_int("-mgb_fuse", &fuse); pbopt_get_int("-mgb_bottom", &bottom); p.no_fuse = !fuse; p.no_bottom = !bottom; }
 	int iters = 0, reason = 0; double seconds = 0.0;
 	if (mgb_solve_pcmg(e, &p, solver->rnorm, &iters, &reason, &seconds) != MGB_OK) die("mgb_solve_pcmg");
 	solver->numIter = iters;

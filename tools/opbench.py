@@ -54,6 +54,8 @@ def main():
                 continue
             if a.ops and op not in a.ops.split(","):
                 continue
+            if op == "bottom_cycle" and (l < 1 or ni > 1023):
+                continue
             ms = e.time_op(op, l, a.reps)
             gbs = bpu * ni * nj / (ms * 1e-3) / 1e9
             own = mgb.FUSED_OWN_BYTES.get(op)

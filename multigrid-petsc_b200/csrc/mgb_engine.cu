@@ -111,6 +111,9 @@ struct Strip {
 	int *status_host = nullptr;
 };
 
+enum { REQ_HALO = 0, REQ_GATHER = 1, REQ_BCAST = 2 };
+struct XferReq { int type, level, phys, depth; };   // a deferred strip-to-strip transfer (see flush_levels)
+
 struct mgb_engine {
 	mgb_config cfg;
 	int P = 1, L = 1, La = 0;                // ranks, levels, first agglomerated level (== L: none)
@@ -128,6 +131,7 @@ struct mgb_engine {
 	cudaGraphExec_t gexec[2] = {nullptr, nullptr};
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
 	int coarse_threshold = 255;              // levels with at most this many rows run in the persistent bottom kernel
+	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
 
@@ -414,7 +418,8 @@ static int check_status(mgb_engine *e)
 	}
 	return MGB_OK;
 }
-static int sync(mgb_engine *e) { TRY(sync_all(e)); return check_status(e); }
+static int flush_all(mgb_engine *e);
+static int sync(mgb_engine *e) { TRY(flush_all(e)); TRY(sync_all(e)); return check_status(e); }
 
 // ------------------------------------------------------------------------------------------------ operators
 extern "C" int mgb_set_level_operator(mgb_engine *e, int level, const double *row_coeff)
@@ -514,98 +519,100 @@ static int xfer_run(mgb_engine *e, std::vector<XferArgs> &args, const std::vecto
 	return MGB_OK;
 }
 
+// Transfer requests are DEFERRED: halo / gather_rows / bcast_rows only record what has to move; flush_levels() turns
+// every pending request that concerns the given levels into ONE k_xfer launch per strip (rows of several vectors and
+// levels travel together, one flag, one wait).  Compute helpers flush the levels they read before launching, so e.g.
+// the ghost rows of u[l] written by the down leg travel together with those of u[l+1] right before the up leg of
+// level l, and a restricted right-hand side travels alone right before the next level's down leg.
+static void add_dst(XferArgs &a, const double *src, double *dst, unsigned long long cnt2, unsigned long long *peer_flag_base, int chan_dummy)
+{
+	(void)chan_dummy;
+	const int d = a.ndst++;
+	a.src[d] = src; a.dst[d] = dst; a.cnt2[d] = cnt2; a.peer_flag[d] = peer_flag_base;   // flag base of the destination rank; channel offset added at flush
+}
+
 // ghost rows of vector `which` on distributed level l: `depth` boundary rows go to each neighbour
 static int halo(mgb_engine *e, int l, int which, int depth)
 {
 	if (e->P == 1 || !e->geo[l].dist) return MGB_OK;
-	const size_t pitch = e->geo[l].pitch;
-	std::vector<XferArgs> args(e->strips.size());
-	std::vector<unsigned long long> tot(e->strips.size(), 0);
-	int chan = 0;
-	for (size_t i = 0; i < e->strips.size(); ++i) {
-		Strip &s = e->strips[i]; SLevel &S = s.lev[l];
-		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
-		const int k = S.phys[which], r = s.rank;
-		chan = CH_HALO(l, k);
-		const unsigned long long cnt2 = (unsigned long long)depth * pitch / 2;
-		if (r > 0) {                                   // my first rows -> the lower ghost rows of rank r-1
-			const int d = a.ndst++;
-			a.src[d] = S.v[which];
-			a.dst[d] = peer_vec(e, r - 1, l, k) + (size_t)e->lay[r - 1].ni[l] * pitch;
-			a.cnt2[d] = cnt2;
-			a.peer_flag[d] = flags_of(e, r - 1) + (size_t)chan * MGB_MAX_RANKS + r;
-			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + (r - 1);
-		}
-		if (r < e->P - 1) {                            // my last rows -> the upper ghost rows of rank r+1
-			const int d = a.ndst++;
-			a.src[d] = S.v[which] + (size_t)(S.ni - depth) * pitch;
-			a.dst[d] = peer_vec(e, r + 1, l, k) - (size_t)depth * pitch;
-			a.cnt2[d] = cnt2;
-			a.peer_flag[d] = flags_of(e, r + 1) + (size_t)chan * MGB_MAX_RANKS + r;
-			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + (r + 1);
-		}
-		tot[i] = cnt2 * a.ndst;
-	}
-	return xfer_run(e, args, tot, chan);
+	e->pending.push_back({REQ_HALO, l, e->strips[0].lev[l].phys[which], depth});
+	return MGB_OK;
 }
-
 // rows [rows[r], rows[r+1]) of vector `which` on the first agglomerated level: every rank -> rank 0
 static int gather_rows(mgb_engine *e, int l, int which)
 {
 	if (e->P == 1) return MGB_OK;
-	const size_t pitch = e->geo[l].pitch;
-	const int chan = CH_GATHER(l);
-	std::vector<XferArgs> args(e->strips.size());
-	std::vector<unsigned long long> tot(e->strips.size(), 0);
-	for (size_t i = 0; i < e->strips.size(); ++i) {
-		Strip &s = e->strips[i]; SLevel &S = s.lev[l];
-		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
-		const int r = s.rank, k = S.phys[which];
-		if (r != 0) {
-			const int c0 = e->geo[l].rows[r], c1 = e->geo[l].rows[r + 1];
-			a.ndst = 1;
-			a.src[0] = S.v[which] + (size_t)c0 * pitch;
-			a.dst[0] = peer_vec(e, 0, l, k) + (size_t)c0 * pitch;
-			a.cnt2[0] = (unsigned long long)(c1 - c0) * pitch / 2;
-			a.peer_flag[0] = flags_of(e, 0) + (size_t)chan * MGB_MAX_RANKS + r;
-			tot[i] = a.cnt2[0];
-		} else {
-			for (int q = 1; q < e->P; ++q) a.wait_flag[a.nwait++] = flags_of(e, 0) + (size_t)chan * MGB_MAX_RANKS + q;
-		}
-	}
-	return xfer_run(e, args, tot, chan);
+	e->pending.push_back({REQ_GATHER, l, e->strips[0].lev[l].phys[which], 0});
+	return MGB_OK;
 }
-
 // rows [rows[r]-3, rows[r+1]+3) of vector `which` on the first agglomerated level: rank 0 -> every rank
 static int bcast_rows(mgb_engine *e, int l, int which)
 {
 	if (e->P == 1) return MGB_OK;
-	const size_t pitch = e->geo[l].pitch;
-	const int chan = CH_BCAST(l);
+	e->pending.push_back({REQ_BCAST, l, e->strips[0].lev[l].phys[which], 0});
+	return MGB_OK;
+}
+
+// launch the pending requests with lo <= level <= hi as one merged exchange
+static int flush_levels(mgb_engine *e, int lo, int hi)
+{
+	if (e->pending.empty()) return MGB_OK;
+	std::vector<XferReq> take, keep;
+	for (auto &q : e->pending) (q.level >= lo && q.level <= hi ? take : keep).push_back(q);
+	if (take.empty()) return MGB_OK;
+	e->pending.swap(keep);
+	int chan = MGB_NCHAN;
+	for (auto &q : take) {
+		const int c = q.type == REQ_HALO ? CH_HALO(q.level, q.phys) : (q.type == REQ_GATHER ? CH_GATHER(q.level) : CH_BCAST(q.level));
+		if (c < chan) chan = c;
+	}
 	std::vector<XferArgs> args(e->strips.size());
 	std::vector<unsigned long long> tot(e->strips.size(), 0);
 	for (size_t i = 0; i < e->strips.size(); ++i) {
-		Strip &s = e->strips[i]; SLevel &S = s.lev[l];
+		Strip &s = e->strips[i];
 		XferArgs &a = args[i]; memset(&a, 0, sizeof a);
-		const int r = s.rank, k = S.phys[which];
-		if (r == 0) {
-			for (int q = 1; q < e->P; ++q) {
-				int c0 = e->geo[l].rows[q] - 3, c1 = e->geo[l].rows[q + 1] + 3;   // the fused up-leg reads 3 coarse ghost rows
-				if (c0 < 0) c0 = 0;
-				if (c1 > e->geo[l].gni) c1 = e->geo[l].gni;
-				const int d = a.ndst++;
-				a.src[d] = S.v[which] + (size_t)c0 * pitch;
-				a.dst[d] = peer_vec(e, q, l, k) + (size_t)c0 * pitch;
-				a.cnt2[d] = (unsigned long long)(c1 - c0) * pitch / 2;
-				a.peer_flag[d] = flags_of(e, q) + (size_t)chan * MGB_MAX_RANKS + 0;
-				tot[i] += a.cnt2[d];
+		const int r = s.rank;
+		unsigned wait_mask = 0;
+		for (auto &q : take) {
+			const int l = q.level, k = q.phys;
+			const size_t pitch = e->geo[l].pitch;
+			double *mine = (double *)(s.arena + e->lay[r].vec_off[l][k]) + e->lay[r].origin[l];
+			if (a.ndst + 8 > MGB_XFER_MAX) return fail(MGB_EINVAL, "too many transfers merged into one exchange");
+			if (q.type == REQ_HALO) {
+				const unsigned long long cnt2 = (unsigned long long)q.depth * pitch / 2;
+				const int ni = e->lay[r].ni[l];
+				if (r > 0) {                               // my first rows -> the lower ghost rows of rank r-1
+					add_dst(a, mine, peer_vec(e, r - 1, l, k) + (size_t)e->lay[r - 1].ni[l] * pitch, cnt2, flags_of(e, r - 1), 0);
+					wait_mask |= 1u << (r - 1);
+				}
+				if (r < e->P - 1) {                        // my last rows -> the upper ghost rows of rank r+1
+					add_dst(a, mine + (size_t)(ni - q.depth) * pitch, peer_vec(e, r + 1, l, k) - (size_t)q.depth * pitch, cnt2, flags_of(e, r + 1), 0);
+					wait_mask |= 1u << (r + 1);
+				}
+			} else if (q.type == REQ_GATHER) {
+				if (r != 0) {
+					const int c0 = e->geo[l].rows[r], c1 = e->geo[l].rows[r + 1];
+					add_dst(a, mine + (size_t)c0 * pitch, peer_vec(e, 0, l, k) + (size_t)c0 * pitch, (unsigned long long)(c1 - c0) * pitch / 2, flags_of(e, 0), 0);
+				} else wait_mask |= ((1u << e->P) - 1u) & ~1u;
+			} else {
+				if (r == 0) {
+					for (int t = 1; t < e->P; ++t) {
+						int c0 = e->geo[l].rows[t] - 3, c1 = e->geo[l].rows[t + 1] + 3;   // the fused up leg reads 3 coarse ghost rows
+						if (c0 < 0) c0 = 0;
+						if (c1 > e->geo[l].gni) c1 = e->geo[l].gni;
+						add_dst(a, mine + (size_t)c0 * pitch, peer_vec(e, t, l, k) + (size_t)c0 * pitch, (unsigned long long)(c1 - c0) * pitch / 2, flags_of(e, t), 0);
+					}
+				} else wait_mask |= 1u;
 			}
-		} else {
-			a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + 0;
 		}
+		// every destination rank gets the flag of this channel raised once per entry (idempotent); waits on the union of sources
+		for (int d = 0; d < a.ndst; ++d) { a.peer_flag[d] += (size_t)chan * MGB_MAX_RANKS + r; tot[i] += a.cnt2[d]; }
+		for (int q = 0; q < e->P; ++q)
+			if (wait_mask & (1u << q)) a.wait_flag[a.nwait++] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + q;
 	}
 	return xfer_run(e, args, tot, chan);
 }
+static int flush_all(mgb_engine *e) { return flush_levels(e, 0, MGB_MAXL); }
 
 // scal[SC_LOCAL .. SC_LOCAL+nvals) of every rank, summed in rank order into scal[slot ..) of every rank
 static int allreduce(mgb_engine *e, int nvals, int slot, int take_sqrt)
@@ -808,6 +815,7 @@ static dim3 stream_grid(const LevelGeom &g, int ni, int ry) { return dim3(cdiv(g
 
 static int k_apply(mgb_engine *e, int l, int xv, int yv)
 {
+	TRY(flush_levels(e, l, l));
 	const LevelGeom &g = e->geo[l];
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
@@ -820,6 +828,7 @@ static int k_apply(mgb_engine *e, int l, int xv, int yv)
 }
 static int k_residual(mgb_engine *e, int l, int xv, int bv, int rv)
 {
+	TRY(flush_levels(e, l, l));
 	const LevelGeom &g = e->geo[l];
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
@@ -846,6 +855,7 @@ static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, in
 // scal[slot] = || b - A x ||_2
 static int k_resnorm(mgb_engine *e, int l, int xv, int bv, int slot)
 {
+	TRY(flush_levels(e, l, l));
 	const LevelGeom &g = e->geo[l];
 	std::vector<int> nb;
 	for (auto &s : e->strips) {
@@ -896,6 +906,7 @@ static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha)
 // scal[first .. first+count) of the first local strip -> its pinned mirror (every rank holds identical values)
 static int read_scalars(mgb_engine *e, int first, int count)
 {
+	TRY(flush_all(e));
 	Strip &s = e->strips[0];
 	CU(cudaMemcpyAsync(s.scal_host + first, s.scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, s.stream));
 	CU(cudaStreamSynchronize(s.stream));
@@ -906,6 +917,7 @@ static double *host_scal(mgb_engine *e) { return e->strips[0].scal_host; }
 // one red-black half sweep of colour c (0 = red: (i+j) even), in place; ghost rows valid on return
 static int k_rb(mgb_engine *e, int l, int xv, int bv, int colour, double omega, int variant)
 {
+	TRY(flush_levels(e, l, l));
 	const LevelGeom &g = e->geo[l];
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
@@ -939,6 +951,7 @@ static int smooth(mgb_engine *e, int l, const mgb_smoother *sm, int its, bool gu
 		int k = 0;
 		if (guess_zero) {
 			if (its <= 0) return vec_zero(e, xv, l);
+			TRY(flush_levels(e, l, l));
 			for (auto &s : e->strips) {
 				if (!computes(s, l)) continue;
 				SLevel &S = s.lev[l];
@@ -950,6 +963,7 @@ static int smooth(mgb_engine *e, int l, const mgb_smoother *sm, int its, bool gu
 			k = 1;
 		}
 		for (; k < its; ++k) {
+			TRY(flush_levels(e, l, l));
 			for (auto &s : e->strips) {
 				if (!computes(s, l)) continue;
 				SLevel &S = s.lev[l];
@@ -1018,6 +1032,7 @@ static LevelDev coarse_view(const mgb_engine *e, const Strip &s, int lc, bool fi
 // gathered on rank 0, otherwise the coarse ghost rows are exchanged.  Needs ghost depth 2 of xv and 1 of bv / rv.
 static int restrict_to_coarse(mgb_engine *e, int l, int bv, int xv, int rv, bool fused)
 {
+	TRY(flush_levels(e, l, l));
 	const LevelGeom &gf = e->geo[l], &gc = e->geo[l + 1];
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
@@ -1038,6 +1053,7 @@ static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 {
 	const LevelGeom &gf = e->geo[l], &gc = e->geo[l + 1];
 	if (gf.dist && !gc.dist) TRY(bcast_rows(e, l + 1, MGB_VEC_U));
+	TRY(flush_levels(e, l, l + 1));
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
 		SLevel &F = s.lev[l], &C = s.lev[l + 1];
@@ -1100,6 +1116,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 		const bool firstc = done == 0, lastc = done + D == its;
 		const int pre_k = firstc ? pre : PRE_GIVEN, post_k = lastc ? post : POST_NONE;
 		std::vector<int> nb;
+		TRY(flush_levels(e, l, (pre_k == PRE_PROLONG || pre_k == PRE_PROLONG_MULTADD) ? l + 1 : l));
 		for (auto &s : e->strips) {
 			if (!computes(s, l)) continue;
 			SLevel &S = s.lev[l];
@@ -1162,6 +1179,7 @@ static int bottom_start(const mgb_engine *e)
 // correction and smoothing up.  b[lp] must be complete on rank 0; on return u[lp] holds the correction.
 static int bottom_cycle(mgb_engine *e, int lp, int its_level, double scale_level, int its_coarse, double scale_coarse, bool multadd)
 {
+	TRY(flush_levels(e, lp, MGB_MAXL));
 	for (auto &s : e->strips) {
 		if (s.rank != 0) continue;
 		CoarseArgs a; memset(&a, 0, sizeof a);
@@ -1345,6 +1363,7 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0));  // :1540-1546
 			}
 		}
+		TRY(flush_all(e));
 		Strip &s0 = e->strips[0];
 		CU(cudaMemcpyAsync(s0.scal_host, s0.scal, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
 		return MGB_OK;
@@ -1359,6 +1378,7 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 		TRY(smooth(e, l, s, p->v0, false, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));                       // :1542
 	}
 	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));                                                // :1545-1546
+	TRY(flush_all(e));
 	Strip &s0 = e->strips[0];
 	CU(cudaMemcpyAsync(s0.scal_host, s0.scal, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
 	return MGB_OK;
@@ -1465,6 +1485,7 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 				return fused_leg(e, l, &p->coarse_smoother, p->coarse_its, PRE_ZERO, POST_NONE, bv, xv, MGB_VEC_W, 0);
 			return smooth(e, l, &p->coarse_smoother, p->coarse_its, true, bv, xv, MGB_VEC_W);
 		}
+		TRY(flush_levels(e, l, l));
 		for (auto &s : e->strips) {
 			if (!computes(s, l)) continue;
 			SLevel &S = s.lev[l];
@@ -1590,6 +1611,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 			if (its >= p->max_iter) { reason = ksp_converged(p, its, dp, &rnorm0, &ttol); if (!reason) reason = -3; }
 		}
 	}
+	TRY(flush_all(e));
 	CU(cudaEventRecord(s0.ev1, s0.stream));
 	TRY(sync_all(e));
 	const auto t1 = std::chrono::steady_clock::now();
@@ -1644,6 +1666,7 @@ extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *m
 			default: return fail(MGB_EINVAL, "unknown op %d", op);
 			}
 		}
+		TRY(flush_all(e));
 		if (pass == 1) CU(cudaEventRecord(s.ev1, s.stream));
 		CU(cudaStreamSynchronize(s.stream));
 	}

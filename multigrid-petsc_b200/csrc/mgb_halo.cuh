@@ -23,14 +23,15 @@
 #include "mgb_common.cuh"
 
 #define MGB_MAX_RANKS 8
+#define MGB_XFER_MAX 24                             // (source, destination) pairs per launch: several vectors travel together
 #define MGB_XFER_THREADS 256
 
 struct XferArgs {
-	int ndst;                                       // destinations of this launch (0..MGB_MAX_RANKS)
-	const double *src[MGB_MAX_RANKS];
-	double *dst[MGB_MAX_RANKS];
-	unsigned long long cnt2[MGB_MAX_RANKS];         // double2 elements to copy per destination
-	unsigned long long *peer_flag[MGB_MAX_RANKS];   // flag word in the destination's memory (its flag[c][my_rank])
+	int ndst;                                       // copies of this launch (0..MGB_XFER_MAX)
+	const double *src[MGB_XFER_MAX];
+	double *dst[MGB_XFER_MAX];
+	unsigned long long cnt2[MGB_XFER_MAX];          // double2 elements per copy
+	unsigned long long *peer_flag[MGB_XFER_MAX];    // flag word in the destination's memory (its flag[c][my_rank])
 	int nwait;
 	const unsigned long long *wait_flag[MGB_MAX_RANKS]; // my own flag words flag[c][src_rank]
 	unsigned long long *ver;                        // my version counter of the channel
@@ -66,9 +67,9 @@ k_xfer(XferArgs a)
 			     k += (unsigned long long)gridDim.x * blockDim.x)
 				t[k] = s[k];
 		}
-		__threadfence_system();
-		__syncthreads();
+		__syncthreads();                              // the block's stores are ordered before thread 0's fence (cumulativity)
 		if (threadIdx.x == 0) {
+			__threadfence_system();
 			const unsigned int t = atomicAdd(a.ticket, 1u);
 			is_last = (t == gridDim.x - 1);
 		}
@@ -88,7 +89,6 @@ k_xfer(XferArgs a)
 		for (int w = 0; w < a.nwait; ++w) {
 			while (ld_acquire_sys(a.wait_flag[w]) < v) {
 				if (clock64() - t0 > a.spin_limit) { atomicExch(a.status, 1); break; }
-				__nanosleep(40);
 			}
 		}
 		__threadfence_system();

@@ -36,7 +36,8 @@ OPS = {"apply": (0, 16), "residual": (1, 24), "jacobi": (2, 24), "rbsor_full": (
        # fused legs: bytes of the UNFUSED sequence they replace (3 x 24 + 18, 18 + 3 x 24 + 16, 3 x 24, 24, 16 + 2 x 24 + 18)
        # and, second number, their own compulsory traffic (read u, b; write u; +2 coarse)
        "fused_down": (11, 90), "fused_up": (12, 106), "fused_3sweeps": (13, 72), "fused_1sweep": (14, 24),
-       "fused_down_zero": (15, 82), "bottom_cycle": (16, 176)}
+       "fused_down_zero": (15, 82), "bottom_cycle": (16, 176),
+       "halo_exchange": (17, 0), "nrm2_allreduce": (18, 8)}
 FUSED_OWN_BYTES = {"fused_down": 26, "fused_up": 26, "fused_3sweeps": 24, "fused_1sweep": 24, "fused_down_zero": 18}
 
 

@@ -1091,14 +1091,17 @@ static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cud
 	return fail(MGB_EINVAL, "fused kernel: combination pre %d / post %d not built", pre, post);
 }
 
-// rows per block of the fused kernel: as many as keep >= ~2 blocks per SM, between 16 and 256, even
+// rows per block of the fused kernel.  The kernel runs 4 blocks per SM (registers and shared memory): 592 resident
+// blocks on 148 SMs.  Large levels get exactly one wave (no partially filled second wave), i.e. as many row chunks as
+// fit next to the column tiles; small levels get chunks of at least 16 rows.
 static int pick_rows(const LevelGeom &g, int ni)
 {
-	const long long tiles = cdiv(g.pitch, FJ_VALID);
-	long long r = (long long)ni * tiles / 592;
-	if (r > 256) r = 256;
+	const int tiles = cdiv(g.pitch, FJ_VALID);
+	int chunks = 592 / tiles;
+	if (chunks < 1) chunks = 1;
+	int r = cdiv(ni, chunks);
 	if (r < 16) r = 16;
-	return (int)(r & ~1LL);
+	return (r + 1) & ~1;
 }
 
 static bool fusable(const mgb_engine *e, const mgb_smoother *sm) { return sm->type == MGB_SMOOTH_JACOBI && !e->cfg.red_black_numbering; }
@@ -1661,12 +1664,14 @@ extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *m
 			case 13: TRY(fused_leg(e, level, &jac, 3, PRE_GIVEN, POST_NONE, B, U, MGB_VEC_W, 0)); break;
 			case 14: TRY(fused_leg(e, level, &jac, 1, PRE_GIVEN, POST_NONE, B, U, MGB_VEC_W, 0)); break;
 			case 15: TRY(fused_leg(e, level, &jac, 3, PRE_ZERO, POST_RESTRICT, B, U, MGB_VEC_W, 0)); break;
+			case 17: TRY(halo(e, level, U, HALO_DEPTH)); TRY(flush_all(e)); break;
+			case 18: TRY(k_reduce(e, level, U, -1, 0, 1)); break;
 			case 16: if (level < 1) return fail(MGB_EINVAL, "the bottom kernel starts at level >= 1");
 			         TRY(bottom_cycle(e, level, 3, 0.8, 3, 0.8, false)); break;
 			default: return fail(MGB_EINVAL, "unknown op %d", op);
 			}
+			TRY(flush_all(e));               // transfers requested by the operation belong to its cost
 		}
-		TRY(flush_all(e));
 		if (pass == 1) CU(cudaEventRecord(s.ev1, s.stream));
 		CU(cudaStreamSynchronize(s.stream));
 	}

@@ -10,7 +10,7 @@
 // Protocol.  Every transfer site is a CHANNEL c with a device-resident version counter ver[c] that all ranks
 // advance in lock step (every rank launches the kernel for every use of a channel, even with nothing to send).
 //   push:  newv = ver[c] + 1; all blocks copy their share; the last block to finish (atomic ticket) issues
-//          __threadfence_system(), stores newv into flag[c][my_rank] of every destination (st.release.sys)
+//          __threadfence_system(), stores newv into flag[c][my_rank] of every destination (st.relaxed.sys)
 //          and sets ver[c] = newv.
 //   wait:  v = ver[c]; spin (ld.acquire.sys) until flag[c][src] >= v for every expected source.
 // In a multi-process run (one strip per process, one GPU each) push and wait are ONE launch: the last block
@@ -48,9 +48,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
 {
-	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+	asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(MGB_XFER_THREADS)
@@ -78,8 +78,8 @@ k_xfer(XferArgs a)
 		if (threadIdx.x == 0) {
 			*a.ticket = 0u;
 			const unsigned long long newv = *a.ver + 1ull;
-			__threadfence_system();
-			for (int d = 0; d < a.ndst; ++d) st_release_sys(a.peer_flag[d], newv);
+			__threadfence_system();                   // one fence, then the flag stores go out back to back (fence + relaxed
+			for (int d = 0; d < a.ndst; ++d) st_relaxed_sys(a.peer_flag[d], newv);   // store = release pattern)
 			*a.ver = newv;
 		}
 	} else if (blockIdx.x != 0) return;

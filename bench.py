@@ -13,7 +13,8 @@ read-back (the reference's loop body).  At N > 1 the same grid is split into N r
   e2e        V-cycles/s through the host C layer (pb200_solve_rhs: the reference-facing Solve() with HOST buffers):
              every solve uploads the right-hand side from pinned host memory, iterates to the reference's
              tolerance (1e-7) and copies the solution back; cycles done / wall time of the calls
-  roofline   the fine-level Jacobi sweep kernel: 24 B per unknown x 8191^2 / CUDA-event time per launch
+  roofline   the dominant kernel = the fused fine-level down leg (3 Jacobi sweeps + residual + restriction in one pass):
+             26 B per unknown x 8191^2 / CUDA-event time per launch; fine_level_ops lists the one-sweep kernels too
   cpu_baseline  the reference's own sources (oracle/_ref/poisson_ref: src/*.c over the in-repo mini-PETSc, real
              PETSc is not in the image) on the host cores, on a bounded sample
   --impl reference   that CPU program on the full workload for a few cycles (rank 0 only)
@@ -38,6 +39,11 @@ LEVELS = 13
 SMOOTHER = "-pc_type jacobi -ksp_richardson_scale 0.8"
 JACOBI_BYTES_PER_UNKNOWN = 24          # SURVEY.md 8d / DESIGN.md: read x, read b, write x
 VCYCLE_BYTES_PER_FINE_UNKNOWN = 264    # unfused per-sweep byte count of a V(3,3) cycle, all levels
+# the dominant kernel of the product path is the fused down leg k_jfused<3,PRE_GIVEN,POST_RESTRICT> on level 0
+# (3 Jacobi sweeps + residual + restriction in one pass): it reads u and b once, writes u once and 1/4 coarse value
+FUSED_DOWN_BYTES_PER_UNKNOWN = 26      # 8 + 8 + 8 + 2
+FUSED_DOWN_UNFUSED_BYTES = 90          # the SURVEY.md 8d count of what it replaces: 3 x 24 (sweeps) + 18 (residual+restrict)
+NCU_TRAFFIC_FUSED_DOWN = 1.770e9       # dram read + write bytes per launch, ncu --set full (profiles/r1_ncu_fused_down.txt)
 
 
 def options(npts, levels, iters, extra=""):
@@ -193,14 +199,15 @@ def b200_arm(a):
     assert it == steps, (it, steps)
     value = steps / (ms * 1e-3)
     peak, peak_kind = hbm_peak()
-    # ---- roofline of the dominant kernel (fine-level Jacobi sweep), CUDA events on the engine's stream
-    t_j = e.time_op("jacobi", 0, 20)
-    ach = JACOBI_BYTES_PER_UNKNOWN * n * n / (t_j * 1e-3) / 1e9
+    # ---- roofline of the dominant kernel (fused down leg on the fine level), CUDA events on the engine's stream
+    t_f = e.time_op("fused_down", 0, 20)
+    ach = FUSED_DOWN_BYTES_PER_UNKNOWN * n * n / (t_f * 1e-3) / 1e9
     per_op = {}
-    for op in ("residual_norm", "residual_restrict", "prolong_correct"):
-        t = e.time_op(op, 0, 20)
-        per_op[op] = {"us": t * 1e3, "gbs": mgb.OPS[op][1] * n * n / (t * 1e-3) / 1e9}
-    per_op["jacobi"] = {"us": t_j * 1e3, "gbs": ach}
+    for op in ("fused_down", "fused_up", "jacobi", "residual", "residual_norm", "residual_restrict", "prolong_correct"):
+        t = t_f if op == "fused_down" else e.time_op(op, 0, 20)
+        per_op[op] = {"us": t * 1e3, "gbs_unfused_count": mgb.OPS[op][1] * n * n / (t * 1e-3) / 1e9}
+        if op in mgb.FUSED_OWN_BYTES:
+            per_op[op]["gbs_own_traffic"] = mgb.FUSED_OWN_BYTES[op] * n * n / (t * 1e-3) / 1e9
     # ---- e2e: reference-facing Solve() with host buffers
     b_host = torch.empty(n * n, dtype=torch.float64, pin_memory=True)
     u_host = torch.empty(n * n, dtype=torch.float64, pin_memory=True)
@@ -234,8 +241,13 @@ def b200_arm(a):
             "config": {"workload": f"2D Poisson {NPTS}^2 fp64, {LEVELS}-level V(3,3), Richardson+Jacobi 0.8 (BASELINE configs[3] at N=1)",
                        "unknowns": n * n, "l2": "inputs larger than L2 (537 MB per fine vector)", "parallelism": "1 strip"},
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_stream5<ST_JACOBI> level 0", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "peak_kind": peak_kind, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "k_jfused<3,PRE_GIVEN,POST_RESTRICT> level 0 (3 Jacobi sweeps + residual + restriction, one pass)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
+                         "traffic": NCU_TRAFFIC_FUSED_DOWN, "algorithmic_bytes_per_launch": FUSED_DOWN_BYTES_PER_UNKNOWN * n * n,
+                         "note": "temporal blocking: the kernel's own compulsory traffic is 26 B/unknown; by the unfused SURVEY 8d count "
+                                 "(90 B/unknown for the 3 sweeps + residual + restriction it replaces) it delivers "
+                                 f"{FUSED_DOWN_UNFUSED_BYTES * n * n / (t_f * 1e-3) / 1e9:.0f} GB/s-equivalent; it is fp64-issue / shared-memory bound, "
+                                 "not HBM bound (DESIGN.md section 4). The one-sweep kernels it replaces are listed in fine_level_ops.",
                          "vcycle_gbs_unfused_count": VCYCLE_BYTES_PER_FINE_UNKNOWN * n * n * value / 1e9,
                          "fine_level_ops": per_op},
             "e2e": {"value": e2e, "unit": "V-cycles/s", "h2d_bytes_per_step": bytes_per_solve * nsolve / cycles,

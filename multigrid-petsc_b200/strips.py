@@ -123,10 +123,12 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
         k_busy += 1
     clocks = clk.stop() if rank == 0 else None
     value = steps / (ms * 1e-3)
-    # dominant kernel on this rank's strip (the launches include the ghost-row push: collective)
+    # dominant kernel on this rank's strip: the fused down leg incl. its ghost-row / coarse-rhs exchange (collective)
     r0, r1 = e.local_rows(0)
-    t_j = _max_over_ranks(e.time_op("jacobi", 0, 20))
-    ach = 24.0 * n * n / (t_j * 1e-3) / 1e9          # aggregate over the N strips
+    dist.barrier()
+    torch.cuda.synchronize()
+    t_j = _max_over_ranks(e.time_op("fused_down", 0, 20))
+    ach = 26.0 * n * n / (t_j * 1e-3) / 1e9          # aggregate over the N strips
     peak, peak_kind = hbm_peak()
     # e2e: every rank uploads its rows of the right-hand side from pinned memory and reads its rows of u back
     b_host = torch.empty(n * n, dtype=torch.float64, pin_memory=True)
@@ -156,7 +158,7 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
                            f"{8.0 * n * n / world / 1e6:.0f} MB", "parallelism": f"{world} row strips, P2P ghost rows over NVLink, "
                            "levels with <= 511 rows agglomerated on rank 0"},
                 "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "k_stream5<ST_JACOBI> level 0 (+ ghost-row push)", "achieved": ach,
+                "roofline": {"bound": "hbm", "kernel": "k_jfused<3,PRE_GIVEN,POST_RESTRICT> level 0 on every strip (+ its ghost-row exchange)", "achieved": ach,
                              "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world), "peak_kind": peak_kind + f" x {world} GPUs",
                              "traffic": None, "vcycle_gbs_unfused_count": 264.0 * n * n * value / 1e9},
                 "e2e": {"value": cycles / t_e2e, "unit": "V-cycles/s", "h2d_bytes_per_step": bytes_per_solve * nsolve / cycles,

@@ -369,7 +369,7 @@ class Session:
         if rc != 0:
             raise MgbError(f"pb200_solve failed ({rc}): {self.H.pb200_last_error().decode()}")
         return {"num_iter": res.num_iter, "rnorm": rn[: res.num_iter + 1].copy(), "error": np.array(res.error[:]),
-                "u": u, "levels": res.levels, "gpu_launches": res.gpu_launches}
+                "u": u, "levels": res.levels, "gpu_launches": res.gpu_launches, "solve_seconds": res.solve_seconds}
 
     def solve_rhs(self, b_ptr, u_ptr):
         """One more Solve() with the right-hand side at host address b_ptr (ni*nj doubles) and the solution copied
@@ -412,4 +412,4 @@ def run_poisson(options, out_dir=None, want_u=True, rnorm_cap=None):
     if rc != 0:
         raise MgbError(f"pb200_run failed ({rc}): {H.pb200_last_error().decode()}")
     return {"num_iter": res.num_iter, "rnorm": rn[: res.num_iter + 1].copy(), "error": np.array(res.error[:]),
-            "u": u, "levels": res.levels, "gpu_launches": res.gpu_launches}
+            "u": u, "levels": res.levels, "gpu_launches": res.gpu_launches, "solve_seconds": res.solve_seconds}

@@ -15,6 +15,7 @@
 
 extern jmp_buf *pb200_trap;
 long long mgb_launch_count(const struct mgb_engine *e);
+double mgb_last_solve_ms(const struct mgb_engine *e);
 
 /* ref: src/poisson.c:165-214 */
 static void print_info(Mesh *mesh, Indices *indices, Operator *op, Solver *solver, int cyc, int meshflag, int mapflag)
@@ -140,6 +141,7 @@ static void session_results(pb200_session *s, pb200_result *res, double *u_out, 
 		memcpy(res->error, s->pp.error, sizeof s->pp.error);
 		res->levels = s->indices.levels;
 		res->gpu_launches = mgb_launch_count(pb200_engine(&s->solver));
+		res->solve_seconds = 1e-3 * mgb_last_solve_ms(pb200_engine(&s->solver));   /* cycle loop only, CUDA events */
 	}
 	if (rnorm_out) for (int k = 0; k <= s->solver.numIter && k < rnorm_cap; k++) rnorm_out[k] = s->solver.rnorm[k];
 	if (u_out) mgb_get_solution(pb200_engine(&s->solver), u_out);

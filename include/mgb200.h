@@ -171,6 +171,13 @@ typedef struct {
  * (src/solver.c:1554-1557).  seconds = wall time of the cycle loop only (src/solver.c:1526-1553). */
 int  mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter, double *seconds);
 
+/* The same solve for a stream of independent right-hand sides, pipelined: the upload of right-hand side k+1 and the
+ * download of solution k-1 overlap with solve k (pinned host memory needed for real overlap).  b_hosts / u_hosts:
+ * nrhs whole-grid host arrays each; num_iter / final_rnorm: nrhs entries (may be NULL); seconds: wall time of the
+ * whole batch including every host<->device copy. */
+int  mgb_solve_vcycle_many(mgb_engine *e, const mgb_vcycle_params *p, int nrhs, const double *const *b_hosts,
+                           double *const *u_hosts, int *num_iter, double *final_rnorm, double *seconds);
+
 #define MGB_KSP_RICHARDSON 0
 #define MGB_KSP_CG         1
 #define MGB_COARSE_LU          0   /* -mg_coarse_ksp_type preonly -mg_coarse_pc_type lu (PCMG default)   */

@@ -122,6 +122,7 @@ def host_lib():
         L.pb200_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.pb200_solve.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(RunResult), C.c_void_p, C.c_void_p, C.c_int]
         L.pb200_solve_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RunResult), C.c_void_p, C.c_int]
+        L.pb200_solve_rhs_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pb200_close.argtypes = [C.c_void_p]
         L.pb200_session_engine.restype = C.c_void_p
         L.pb200_session_engine.argtypes = [C.c_void_p]
@@ -381,6 +382,21 @@ class Session:
         if rc != 0:
             raise MgbError(f"pb200_solve_rhs failed ({rc}): {self.H.pb200_last_error().decode()}")
         return {"num_iter": res.num_iter, "rnorm": rn[: res.num_iter + 1].copy(), "gpu_launches": res.gpu_launches}
+
+    def solve_rhs_many(self, b_ptrs, u_ptrs):
+        """Solve() for a stream of right-hand sides (host addresses, whole-grid arrays, ideally pinned): uploads,
+        solves and downloads are pipelined.  Returns (iterations per solve, final relative residuals, seconds)."""
+        n = len(b_ptrs)
+        assert n == len(u_ptrs) and n >= 1
+        B = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in b_ptrs])
+        U = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in u_ptrs])
+        its = (C.c_int * n)()
+        fin = (C.c_double * n)()
+        sec = C.c_double()
+        rc = self.H.pb200_solve_rhs_many(self.s, n, B, U, its, fin, C.byref(sec))
+        if rc != 0:
+            raise MgbError(f"pb200_solve_rhs_many failed ({rc}): {self.H.pb200_last_error().decode()}")
+        return list(its), list(fin), sec.value
 
     def close(self):
         if getattr(self, "s", None):

@@ -107,3 +107,32 @@ __global__ void k_error2(const double *__restrict__ partial, int n, double *__re
 	for (int k = 0; k < n; ++k) { m = fmax(m, partial[3 * k]); s1 += partial[3 * k + 1]; s2 += partial[3 * k + 2]; }
 	out[0] = m; out[1] = s1; out[2] = finalize ? sqrt(s2) : s2;
 }
+
+// Host arrays are dense (row length nj), level vectors are pitched: PCIe copies go through a dense staging buffer
+// (a pitched cudaMemcpy2D from host memory runs at half the link rate) and these kernels repack at HBM speed.
+__global__ void __launch_bounds__(256)
+k_unpack_rows(double *__restrict__ v, const double *__restrict__ dense, int ni, int nj, int pitch)
+{
+	const size_t total = (size_t)ni * nj;
+	for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+		const size_t i = k / nj, j = k - i * nj;
+		v[i * pitch + j] = dense[k];
+	}
+}
+__global__ void __launch_bounds__(256)
+k_pack_rows(double *__restrict__ dense, const double *__restrict__ v, int ni, int nj, int pitch)
+{
+	const size_t total = (size_t)ni * nj;
+	for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+		const size_t i = k / nj, j = k - i * nj;
+		dense[k] = v[i * pitch + j];
+	}
+}
+
+// device scalars -> mapped pinned host memory by a kernel store: the per-cycle read-back of the residual norm must
+// not queue on a copy engine behind a half-gigabyte upload or download that overlaps the solve
+__global__ void k_publish(double *__restrict__ host_mapped, const double *__restrict__ dev, int first, int count)
+{
+	if ((int)threadIdx.x < count) host_mapped[first + threadIdx.x] = dev[first + threadIdx.x];
+	__threadfence_system();
+}

@@ -106,11 +106,17 @@ struct Strip {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double *partial = nullptr; size_t partial_cap = 0;
-	double *scal = nullptr, *scal_host = nullptr;
+	double *scal = nullptr, *scal_host = nullptr, *scal_host_dev = nullptr;   // device scalars, mapped pinned mirror (+ its device alias)
 	double *tab_x = nullptr, *tab_y = nullptr;
 	int *status_host = nullptr;
+	double *stage_in = nullptr, *stage_out = nullptr;     // dense staging buffers for PCIe copies of large vectors (lazy)
+	size_t stage_cap = 0;
+	cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host <-> device copies overlapped with a solve (mgb_solve_vcycle_many)
+	cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_sol = nullptr;
 };
 
+struct PtrState { double *v[MGB_MAXL][MGB_NVEC]; int phys[MGB_MAXL][MGB_NVEC]; };
+struct GraphEntry { std::vector<char> key; cudaGraphExec_t exec; long long launches; std::vector<PtrState> after; };
 enum { REQ_HALO = 0, REQ_GATHER = 1, REQ_BCAST = 2 };
 struct XferReq { int type, level, phys, depth; };   // a deferred strip-to-strip transfer (see flush_levels)
 
@@ -128,12 +134,13 @@ struct mgb_engine {
 	long long launches = 0;
 	double last_solve_ms = 0.0;
 	bool csr_built = false;
-	cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+	std::vector<struct GraphEntry> gcache;   // instantiated V-cycle graphs, keyed by parameters + pointer state
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
 	int coarse_threshold = 255;              // levels with at most this many rows run in the persistent bottom kernel
 	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
+static void drop_graphs(mgb_engine *e);
 
 // ------------------------------------------------------------------------------------------------ partition + layout
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -262,15 +269,21 @@ extern "C" int mgb_destroy(mgb_engine *e)
 {
 	if (!e) return MGB_OK;
 	for (auto &s : e->strips) if (s.stream) cudaStreamSynchronize(s.stream);
-	for (int g = 0; g < 2; ++g) if (e->gexec[g]) cudaGraphExecDestroy(e->gexec[g]);
+	for (auto &g : e->gcache) cudaGraphExecDestroy(g.exec);
 	for (int r = 0; r < MGB_MAX_RANKS; ++r) if (e->peer_opened[r]) cudaIpcCloseMemHandle(e->arena_of[r]);
 	for (size_t i = 0; i < e->strips.size(); ++i) {
 		Strip &s = e->strips[i];
 		for (auto &L : s.lev) { cudaFree(L.coef); free_csr(L.A); free_csr(L.R); free_csr(L.P); bandlu_free(L.lu); }
+		cudaFree(s.stage_in); cudaFree(s.stage_out);
 		cudaFree(s.arena); cudaFree(s.partial); cudaFree(s.scal); cudaFreeHost(s.scal_host); cudaFreeHost(s.status_host);
 		cudaFree(s.tab_x); cudaFree(s.tab_y);
 		if (s.ev0) cudaEventDestroy(s.ev0);
 		if (s.ev1) cudaEventDestroy(s.ev1);
+		if (s.ev_in) cudaEventDestroy(s.ev_in);
+		if (s.ev_out) cudaEventDestroy(s.ev_out);
+		if (s.ev_sol) cudaEventDestroy(s.ev_sol);
+		if (s.copy_in) cudaStreamDestroy(s.copy_in);
+		if (s.copy_out) cudaStreamDestroy(s.copy_out);
 		if (s.stream && i == 0) cudaStreamDestroy(s.stream);       // emulated strips share the stream of strip 0
 	}
 	delete e;
@@ -308,6 +321,9 @@ extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
 		if (i == 0) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
 		else s.stream = e->strips[0].stream;                       // emulation: one stream, lock step
 		CU(cudaEventCreate(&s.ev0)); CU(cudaEventCreate(&s.ev1));
+		CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&s.ev_sol, cudaEventDisableTiming));
+		CU(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
 		CU(cudaMalloc(&s.arena, y.total));
 		CU(cudaMemsetAsync(s.arena, 0, y.total, s.stream));
 		e->arena_of[s.rank] = s.arena;
@@ -335,7 +351,8 @@ extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
 		CU(cudaMalloc(&s.partial, sizeof(double) * nb));
 		CU(cudaMalloc(&s.scal, sizeof(double) * 64));
 		CU(cudaMemsetAsync(s.scal, 0, sizeof(double) * 64, s.stream));
-		CU(cudaMallocHost(&s.scal_host, sizeof(double) * 64));
+		CU(cudaHostAlloc(&s.scal_host, sizeof(double) * 64, cudaHostAllocMapped));
+		CU(cudaHostGetDevicePointer(&s.scal_host_dev, s.scal_host, 0));
 		CU(cudaMallocHost(&s.status_host, sizeof(int) * 4));
 		s.status_host[0] = 0;
 		CU(cudaMalloc(&s.tab_x, sizeof(double) * (size_t)(cfg->nj + 16)));
@@ -440,6 +457,7 @@ extern "C" int mgb_set_level_operator(mgb_engine *e, int level, const double *ro
 	g.coef_set = true;
 	e->sor_omega = 1.0;
 	e->csr_built = false;
+	drop_graphs(e);
 	for (auto &s : e->strips) {
 		SLevel &S = s.lev[level];
 		bandlu_free(S.lu);
@@ -480,6 +498,7 @@ extern "C" int mgb_set_transfer(mgb_engine *e, const double res3[9], const doubl
 	}
 	e->transfer_set = true;
 	e->csr_built = false;
+	drop_graphs(e);
 	return MGB_OK;
 }
 
@@ -729,6 +748,53 @@ extern "C" int mgb_csr_get(const mgb_engine *e, int which, int level, int *rowpt
 }
 
 // ------------------------------------------------------------------------------------------------ vectors
+// rows of a level vector <- dense host rows (host points at this strip's first row).  Large vectors go through a
+// dense staging buffer + repack kernel; `st` is the stream everything is enqueued on.
+#define STAGE_MIN_BYTES (4u << 20)
+static int stage_alloc(mgb_engine *e, Strip &s)
+{
+	const size_t need = (size_t)s.lev[0].ni * e->geo[0].nj;
+	if (s.stage_cap >= need) return MGB_OK;
+	cudaFree(s.stage_in); cudaFree(s.stage_out); s.stage_in = s.stage_out = nullptr; s.stage_cap = 0;
+	CU(cudaMalloc(&s.stage_in, need * sizeof(double)));
+	CU(cudaMalloc(&s.stage_out, need * sizeof(double)));
+	s.stage_cap = need;
+	return MGB_OK;
+}
+static int put_rows(mgb_engine *e, Strip &s, int level, int which, const double *host, cudaStream_t st)
+{
+	const LevelGeom &g = e->geo[level]; SLevel &S = s.lev[level];
+	const size_t bytes = (size_t)S.ni * g.nj * sizeof(double);
+	if (level != 0 || bytes < STAGE_MIN_BYTES) {
+		CU(cudaMemcpy2DAsync(S.v[which], sizeof(double) * g.pitch, host, sizeof(double) * g.nj, sizeof(double) * g.nj, S.ni,
+		                     cudaMemcpyHostToDevice, st));
+		return MGB_OK;
+	}
+	TRY(stage_alloc(e, s));
+	CU(cudaMemcpyAsync(s.stage_in, host, bytes, cudaMemcpyHostToDevice, st));
+	k_unpack_rows<<<148 * 8, 256, 0, st>>>(S.v[which], s.stage_in, S.ni, g.nj, g.pitch);
+	LAUNCHED(e); KCHECK();
+	return MGB_OK;
+}
+// dense host rows <- rows of a level vector; the pack kernel runs on `kst`, the PCIe copy on `cst` (after `ev`)
+static int get_rows(mgb_engine *e, Strip &s, int level, int which, double *host, cudaStream_t kst, cudaStream_t cst, cudaEvent_t ev)
+{
+	const LevelGeom &g = e->geo[level]; SLevel &S = s.lev[level];
+	const size_t bytes = (size_t)S.ni * g.nj * sizeof(double);
+	if (level != 0 || bytes < STAGE_MIN_BYTES) {
+		if (cst != kst) { CU(cudaEventRecord(ev, kst)); CU(cudaStreamWaitEvent(cst, ev, 0)); }
+		CU(cudaMemcpy2DAsync(host, sizeof(double) * g.nj, S.v[which], sizeof(double) * g.pitch, sizeof(double) * g.nj, S.ni,
+		                     cudaMemcpyDeviceToHost, cst));
+		return MGB_OK;
+	}
+	TRY(stage_alloc(e, s));
+	k_pack_rows<<<148 * 8, 256, 0, kst>>>(s.stage_out, S.v[which], S.ni, g.nj, g.pitch);
+	LAUNCHED(e); KCHECK();
+	if (cst != kst) { CU(cudaEventRecord(ev, kst)); CU(cudaStreamWaitEvent(cst, ev, 0)); }
+	CU(cudaMemcpyAsync(host, s.stage_out, bytes, cudaMemcpyDeviceToHost, cst));
+	return MGB_OK;
+}
+
 // Host vectors are whole-grid arrays (gni x nj, natural order).  Every local strip moves its own rows; in a
 // one-strip-per-process run the other rows of the host array are neither read nor written.
 extern "C" int mgb_vec_set(mgb_engine *e, int which, int level, const double *host)
@@ -739,8 +805,7 @@ extern "C" int mgb_vec_set(mgb_engine *e, int which, int level, const double *ho
 	for (auto &s : e->strips) {
 		SLevel &S = s.lev[level];
 		if (!S.present || !S.active) continue;
-		CU(cudaMemcpy2DAsync(S.v[which], sizeof(double) * g.pitch, host + (size_t)S.r0 * g.nj, sizeof(double) * g.nj,
-		                     sizeof(double) * g.nj, S.ni, cudaMemcpyHostToDevice, s.stream));
+		TRY(put_rows(e, s, level, which, host + (size_t)S.r0 * g.nj, s.stream));
 	}
 	return sync_all(e);
 }
@@ -752,8 +817,7 @@ extern "C" int mgb_vec_get(mgb_engine *e, int which, int level, double *host)
 	for (auto &s : e->strips) {
 		SLevel &S = s.lev[level];
 		if (!S.present || !S.active) continue;
-		CU(cudaMemcpy2DAsync(host + (size_t)S.r0 * g.nj, sizeof(double) * g.nj, S.v[which], sizeof(double) * g.pitch,
-		                     sizeof(double) * g.nj, S.ni, cudaMemcpyDeviceToHost, s.stream));
+		TRY(get_rows(e, s, level, which, host + (size_t)S.r0 * g.nj, s.stream, s.stream, s.ev_sol));
 	}
 	return sync_all(e);
 }
@@ -908,7 +972,8 @@ static int read_scalars(mgb_engine *e, int first, int count)
 {
 	TRY(flush_all(e));
 	Strip &s = e->strips[0];
-	CU(cudaMemcpyAsync(s.scal_host + first, s.scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, s.stream));
+	k_publish<<<1, 32, 0, s.stream>>>(s.scal_host_dev, s.scal, first, count);
+	LAUNCHED(e); KCHECK();
 	CU(cudaStreamSynchronize(s.stream));
 	return MGB_OK;
 }
@@ -1230,7 +1295,8 @@ extern "C" int mgb_error_norms_separable(mgb_engine *e, const double *sx, const 
 		LAUNCHED(e); KCHECK();
 		k_error2<<<1, 32, 0, s.stream>>>(s.partial, blocks, s.scal + 8, multi ? 0 : 1);
 		LAUNCHED(e); KCHECK();
-		CU(cudaMemcpyAsync(s.scal_host + 8, s.scal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+		k_publish<<<1, 32, 0, s.stream>>>(s.scal_host_dev, s.scal, 8, 3);
+		LAUNCHED(e); KCHECK();
 		CU(cudaStreamSynchronize(s.stream));
 		mx = fmax(mx, s.scal_host[8]); s1 += s.scal_host[9]; s2 += s.scal_host[10];
 	}
@@ -1368,7 +1434,8 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 		}
 		TRY(flush_all(e));
 		Strip &s0 = e->strips[0];
-		CU(cudaMemcpyAsync(s0.scal_host, s0.scal, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+		k_publish<<<1, 32, 0, s0.stream>>>(s0.scal_host_dev, s0.scal, 0, 1);
+		LAUNCHED(e); KCHECK();
 		return MGB_OK;
 	}
 	TRY(smooth(e, 0, s, p->v0, first, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));                          // :1531-1532
@@ -1383,16 +1450,17 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));                                                // :1545-1546
 	TRY(flush_all(e));
 	Strip &s0 = e->strips[0];
-	CU(cudaMemcpyAsync(s0.scal_host, s0.scal, sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+	k_publish<<<1, 32, 0, s0.stream>>>(s0.scal_host_dev, s0.scal, 0, 1);
+	LAUNCHED(e); KCHECK();
 	return MGB_OK;
 }
 
 static void drop_graphs(mgb_engine *e)
 {
-	for (int g = 0; g < 2; ++g) if (e->gexec[g]) { cudaGraphExecDestroy(e->gexec[g]); e->gexec[g] = nullptr; }
+	for (auto &g : e->gcache) cudaGraphExecDestroy(g.exec);
+	e->gcache.clear();
 }
 
-struct PtrState { double *v[MGB_MAXL][MGB_NVEC]; int phys[MGB_MAXL][MGB_NVEC]; };
 static void save_state(mgb_engine *e, std::vector<PtrState> &st)
 {
 	st.resize(e->strips.size());
@@ -1406,71 +1474,153 @@ static void load_state(mgb_engine *e, const std::vector<PtrState> &st)
 		for (int l = 0; l < e->L; ++l)
 			for (int k = 0; k < MGB_NVEC; ++k) { e->strips[i].lev[l].v[k] = st[i].v[l][k]; e->strips[i].lev[l].phys[k] = st[i].phys[l][k]; }
 }
-
-extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter, double *seconds)
+// A captured cycle is valid for one set of parameters and one assignment of the ping-pong pointers: that is the key.
+static std::vector<char> graph_key(mgb_engine *e, const mgb_vcycle_params *p)
 {
-	NEED(e);
-	if (!p || !rnorm || !num_iter) return fail(MGB_EINVAL, "null argument");
-	TRY(require_ops(e, true)); TRY(check_smoother(e, &p->smoother));
-	if (p->v0 < 0 || p->v1 < 0 || p->max_iter < 0) return fail(MGB_EINVAL, "negative sweep or iteration count");
+	std::vector<char> k(sizeof *p);
+	memcpy(k.data(), p, sizeof *p);
+	for (auto &s : e->strips)
+		for (int l = 0; l < e->L; ++l) {
+			const char *b = (const char *)s.lev[l].v;
+			k.insert(k.end(), b, b + sizeof s.lev[l].v);
+		}
+	return k;
+}
+
+// the cycle loop of MultigridVcycle on the right-hand side in B[0] (ref: src/solver.c:1512-1558); rnorm holds
+// max_iter+1 entries and is returned normalised by rnorm[0]
+static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter)
+{
 	Strip &s0 = e->strips[0];
 	// bnorm = ||b0|| ; u0 = 0 ; rnorm[0] = ||A0 u0 - b0||                                      (:1512-1520)
 	TRY(halo(e, 0, MGB_VEC_B, HALO_DEPTH));
 	TRY(k_reduce(e, 0, MGB_VEC_B, -1, 1, 1));
 	TRY(vec_zero(e, MGB_VEC_U, 0));
 	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));
-	TRY(read_scalars(e, 0, 2)); TRY(sync(e));
+	TRY(read_scalars(e, 0, 2));
 	const double bnorm = host_scal(e)[1];
 	double rn = host_scal(e)[0];
 	rnorm[0] = rn;
 	int iter = 0;
-	drop_graphs(e);
-	long long launches_per_graph[2] = {0, 0};
-	std::vector<PtrState> state_after[2];
-	const auto t0 = std::chrono::steady_clock::now();
-	CU(cudaEventRecord(s0.ev0, s0.stream));
-	int gphase = 0;
+	if (e->gcache.size() > 16) drop_graphs(e);
 	while (iter < p->max_iter && 100000000.0 * bnorm > rn && rn > p->rtol * bnorm) {              // :1530
 		if (!p->use_graph || iter == 0) {
 			TRY(vcycle_body(e, p, iter == 0));
 		} else {
-			if (!e->gexec[gphase]) {
-				// capture this phase: the pointer state before/after is a pure function of the phase
-				cudaGraph_t g;
+			const std::vector<char> key = graph_key(e, p);
+			GraphEntry *g = nullptr;
+			for (auto &c : e->gcache) if (c.key == key) { g = &c; break; }
+			if (!g) {
+				// capture: the pointer state after the cycle is a pure function of the state before it
+				cudaGraph_t graph;
 				const long long l0 = e->launches;
 				CU(cudaStreamBeginCapture(s0.stream, cudaStreamCaptureModeThreadLocal));
 				int r = vcycle_body(e, p, false);
-				cudaError_t ce = cudaStreamEndCapture(s0.stream, &g);
+				cudaError_t ce = cudaStreamEndCapture(s0.stream, &graph);
 				if (r != MGB_OK) return r;
 				if (ce != cudaSuccess) return fail(MGB_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-				CU(cudaGraphInstantiate(&e->gexec[gphase], g, 0));
-				cudaGraphDestroy(g);
-				launches_per_graph[gphase] = e->launches - l0;
+				GraphEntry ne; ne.key = key; ne.exec = nullptr;
+				CU(cudaGraphInstantiate(&ne.exec, graph, 0));
+				cudaGraphDestroy(graph);
+				ne.launches = e->launches - l0;
 				e->launches = l0;
-				save_state(e, state_after[gphase]);
+				save_state(e, ne.after);
+				e->gcache.push_back(ne);
+				g = &e->gcache.back();
 			} else {
-				load_state(e, state_after[gphase]);
+				load_state(e, g->after);
 			}
-			CU(cudaGraphLaunch(e->gexec[gphase], s0.stream));
-			e->launches += launches_per_graph[gphase];
-			gphase ^= 1;
+			CU(cudaGraphLaunch(g->exec, s0.stream));
+			e->launches += g->launches;
 		}
 		CU(cudaStreamSynchronize(s0.stream));
 		rn = s0.scal_host[0];
 		iter = iter + 1;
 		rnorm[iter] = rn;
 	}
+	const double r0 = rnorm[0];
+	for (int i = 0; i <= iter; ++i) rnorm[i] = rnorm[i] / r0;                                     // :1554-1557
+	*num_iter = iter;
+	return MGB_OK;
+}
+
+static int vcycle_check(mgb_engine *e, const mgb_vcycle_params *p)
+{
+	TRY(require_ops(e, true)); TRY(check_smoother(e, &p->smoother));
+	if (p->v0 < 0 || p->v1 < 0 || p->max_iter < 0) return fail(MGB_EINVAL, "negative sweep or iteration count");
+	return MGB_OK;
+}
+
+extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter, double *seconds)
+{
+	NEED(e);
+	if (!p || !rnorm || !num_iter) return fail(MGB_EINVAL, "null argument");
+	TRY(vcycle_check(e, p));
+	Strip &s0 = e->strips[0];
+	TRY(sync(e));
+	const auto t0 = std::chrono::steady_clock::now();
+	CU(cudaEventRecord(s0.ev0, s0.stream));
+	TRY(vcycle_solve(e, p, rnorm, num_iter));
 	CU(cudaEventRecord(s0.ev1, s0.stream));
 	CU(cudaStreamSynchronize(s0.stream));
 	const auto t1 = std::chrono::steady_clock::now();
 	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
 	{ float ms = 0.f; CU(cudaEventElapsedTime(&ms, s0.ev0, s0.ev1)); e->last_solve_ms = ms; }
-	drop_graphs(e);
-	TRY(check_status(e));
-	const double r0 = rnorm[0];
-	for (int i = 0; i <= iter; ++i) rnorm[i] = rnorm[i] / r0;                                     // :1554-1557
-	*num_iter = iter;
-	return MGB_OK;
+	return check_status(e);
+}
+
+// A stream of independent right-hand sides (host arrays, whole-grid, natural order; pinned memory for real overlap):
+// while solve k runs, the right-hand side of solve k+1 is uploaded into a spare level-0 vector and the solution of
+// solve k-1 is downloaded from another one, on two copy streams (both PCIe directions busy, the SMs never wait).
+// The reference's driver solves one right-hand side per process run (ref: src/poisson.c:118-125: Assemble, Solve,
+// GetSol); this is the same Solve() applied to many, with the operator assembled once.
+extern "C" int mgb_solve_vcycle_many(mgb_engine *e, const mgb_vcycle_params *p, int nrhs, const double *const *b_hosts,
+                                     double *const *u_hosts, int *num_iter, double *final_rnorm, double *seconds)
+{
+	NEED(e);
+	if (!p || nrhs < 1 || !b_hosts || !u_hosts) return fail(MGB_EINVAL, "null argument");
+	TRY(vcycle_check(e, p));
+	const LevelGeom &g = e->geo[0];
+	const int SPARE_B = MGB_VEC_Q;                           // a Krylov work vector, idle in cycle 0
+	std::vector<double> rn((size_t)p->max_iter + 2);
+	auto upload = [&](const double *host, int which, bool async) -> int {
+		for (auto &s : e->strips) {
+			SLevel &S = s.lev[0];
+			TRY(put_rows(e, s, 0, which, host + (size_t)S.r0 * g.nj, async ? s.copy_in : s.stream));
+			if (async) CU(cudaEventRecord(s.ev_in, s.copy_in));
+		}
+		return MGB_OK;
+	};
+	TRY(sync(e));
+	const auto t0 = std::chrono::steady_clock::now();
+	const bool trace = getenv("MGB_TRACE") != nullptr;
+	auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+	TRY(upload(b_hosts[0], MGB_VEC_B, false));
+	for (int k = 0; k < nrhs; ++k) {
+		if (trace) fprintf(stderr, "[mgb] rhs %d: t=%.2f ms upload of next issued\n", k, now_ms());
+		if (k + 1 < nrhs) TRY(upload(b_hosts[k + 1], SPARE_B, true));
+		int it = 0;
+		if (trace) fprintf(stderr, "[mgb] rhs %d: t=%.2f ms solve starts\n", k, now_ms());
+		TRY(vcycle_solve(e, p, rn.data(), &it));
+		if (trace) fprintf(stderr, "[mgb] rhs %d: t=%.2f ms solve done (%d cycles)\n", k, now_ms(), it);
+		if (num_iter) num_iter[k] = it;
+		if (final_rnorm) final_rnorm[k] = rn[it];
+		// solution k: packed into the dense staging buffer on the compute stream (after the previous download has left
+		// it), then device-to-host on the second copy stream
+		for (auto &s : e->strips) {
+			SLevel &S = s.lev[0];
+			CU(cudaStreamWaitEvent(s.stream, s.ev_out, 0));
+			TRY(get_rows(e, s, 0, MGB_VEC_U, u_hosts[k] + (size_t)S.r0 * g.nj, s.stream, s.copy_out, s.ev_sol));
+			CU(cudaEventRecord(s.ev_out, s.copy_out));
+			// the next right-hand side must have arrived before it becomes B
+			if (k + 1 < nrhs) CU(cudaStreamWaitEvent(s.stream, s.ev_in, 0));
+		}
+		if (k + 1 < nrhs) swap_vec(e, 0, MGB_VEC_B, SPARE_B);
+	}
+	for (auto &s : e->strips) { CU(cudaStreamSynchronize(s.copy_out)); CU(cudaStreamSynchronize(s.stream)); }
+	const auto t1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	return check_status(e);
 }
 
 // ------------------------------------------------------------------------------------------------ cycle 8

@@ -176,6 +176,8 @@ int  pb200_open(const char *options, pb200_session **out);
 int  pb200_solve(pb200_session *s, const char *dir, pb200_result *res, double *u, double *rnorm, int rnorm_cap);
 /* another solve on the assembled session: b (host, ni*nj) replaces the right-hand side, u (host) receives the solution */
 int  pb200_solve_rhs(pb200_session *s, const double *b, double *u, pb200_result *res, double *rnorm, int rnorm_cap);
+/* a stream of right-hand sides through the same Solve(): copies and solves pipelined; iters/finals: nrhs entries */
+int  pb200_solve_rhs_many(pb200_session *s, int nrhs, const double *const *b, double *const *u, int *iters, double *finals, double *seconds);
 void pb200_close(pb200_session *s);
 struct mgb_engine *pb200_session_engine(pb200_session *s);
 const char *pb200_last_error(void);

@@ -222,6 +222,24 @@ int pb200_solve_rhs(pb200_session *s, const double *b, double *u, pb200_result *
 	return rc;
 }
 
+/* the same for a stream of right-hand sides: uploads, solves and downloads are pipelined (mgb_solve_vcycle_many) */
+int pb200_solve_many_impl(Solver *solver, int nrhs, const double *const *b, double *const *u, int *iters, double *finals, double *seconds);
+int pb200_solve_rhs_many(pb200_session *s, int nrhs, const double *const *b, double *const *u, int *iters, double *finals, double *seconds)
+{
+	jmp_buf trap;
+	if (!s || !b || !u || nrhs < 1) return 2;
+	const int saved = quiet_begin();
+	int rc = 0;
+	pb200_trap = &trap;
+	if (setjmp(trap) == 0) {
+		s->solver.numIter = s->max_iter;
+		rc = pb200_solve_many_impl(&s->solver, nrhs, b, u, iters, finals, seconds);
+	} else rc = 1;
+	pb200_trap = NULL;
+	quiet_end(saved);
+	return rc;
+}
+
 void pb200_close(pb200_session *s)
 {
 	if (!s) return;

@@ -206,9 +206,9 @@ static void read_smoother(const char *prefix, int rb_numbering, mgb_smoother *s,
 }
 
 /* ---------------------------------------------------------------- solve */
-static void solve_vcycle(Solver *solver)
+/* what the level KSPs of cycle 0 are configured with (ref: src/solver.c:1463-1510 + KSPSetFromOptions) */
+static void vcycle_params(Solver *solver, mgb_vcycle_params *pp)
 {
-	mgb_engine *e = ENGINE(solver->assem);
 	int map_style = 2; pbopt_get_int("-map", &map_style);
 	mgb_vcycle_params p;
 	memset(&p, 0, sizeof p);
@@ -229,6 +229,14 @@ static void solve_vcycle(Solver *solver)
 	p.use_graph = 1;
 	pbopt_get_int("-mgb_graph", &p.use_graph);
 	{ int fuse = 1, bottom = 1; pbopt_get_int("-mgb_fuse", &fuse); pbopt_get_int("-mgb_bottom", &bottom); p.no_fuse = !fuse; p.no_bottom = !bottom; }
+	*pp = p;
+}
+
+static void solve_vcycle(Solver *solver)
+{
+	mgb_engine *e = ENGINE(solver->assem);
+	mgb_vcycle_params p;
+	vcycle_params(solver, &p);
 	int iters = 0; double seconds = 0.0;
 	const clock_t c0 = clock();
 	if (mgb_solve_vcycle(e, &p, solver->rnorm, &iters, &seconds) != MGB_OK) die("mgb_solve_vcycle");
@@ -281,6 +289,16 @@ static void solve_pcmg(Solver *solver)
 	solver->numIter = iters;
 	printf("rank = [%d]; Solver walltime:               %lf\n", 0, seconds);
 	printf("KSP converged reason: %d\n", reason);
+}
+
+/* B200 extension: Solve() for a stream of right-hand sides (cycle 0), host<->device copies overlapped with the solves */
+int pb200_solve_many_impl(Solver *solver, int nrhs, const double *const *b, double *const *u, int *iters, double *finals, double *seconds)
+{
+	if (solver->cycle != VCYCLE) refuse("the pipelined multi-right-hand-side solve is offered for -cycle 0");
+	mgb_vcycle_params p;
+	vcycle_params(solver, &p);
+	if (mgb_solve_vcycle_many(ENGINE(solver->assem), &p, nrhs, b, u, iters, finals, seconds) != MGB_OK) die("mgb_solve_vcycle_many");
+	return 0;
 }
 
 void Solve(Solver *solver)

@@ -393,3 +393,33 @@ def test_fused_legs_bit_identical_to_unfused(opts, ranks):
     else:
         assert a["u"].tobytes() == b["u"].tobytes()
         assert np.allclose(a["rnorm"], b["rnorm"], rtol=1e-12, atol=RNORM_ATOL, equal_nan=True)
+
+
+# ------------------------------------------------------------------ pipelined stream of right-hand sides
+@pytest.mark.parametrize("extra", ["", " -mgb_ranks 2 -mgb_emulate 1 -mgb_agglomerate 31"])
+def test_solve_rhs_many_matches_single_solves(extra):
+    """mgb_solve_vcycle_many overlaps the copies of neighbouring solves with the running one; every solution must be
+    bit-identical to the one-at-a-time Solve() on the same right-hand side."""
+    opts = base(257, 8, it=100) + " " + JAC + " -mgb_csr 0" + extra
+    n = 255
+    rng = np.random.default_rng(5)
+    bs = [np.ascontiguousarray(rng.uniform(-1, 1, (n, n))) for _ in range(4)]
+    s = mgb.Session(opts)
+    try:
+        singles = []
+        for b in bs:
+            u = np.zeros((n, n))
+            r = s.solve_rhs(b.ctypes.data, u.ctypes.data)
+            singles.append((r["num_iter"], r["rnorm"][-1], u))
+        us = [np.zeros((n, n)) for _ in bs]
+        its, fin, sec = s.solve_rhs_many([b.ctypes.data for b in bs], [u.ctypes.data for u in us])
+        for k in range(len(bs)):
+            assert its[k] == singles[k][0]
+            assert fin[k] == pytest.approx(singles[k][1], rel=1e-12)
+            assert us[k].tobytes() == singles[k][2].tobytes()
+        # and once more on the same session (graph cache, swapped spare vectors)
+        its2, _, _ = s.solve_rhs_many([b.ctypes.data for b in bs[:3]], [u.ctypes.data for u in us[:3]])
+        assert its2 == its[:3]
+        assert us[2].tobytes() == singles[2][2].tobytes()
+    finally:
+        s.close()

@@ -171,6 +171,9 @@ def b200_arm(a):
         raise SystemExit(f"bench.py: --gpus {a.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run --nproc-per-node {a.gpus}")
     torch.cuda.set_device(local)
     mgb = importlib.import_module("multigrid-petsc_b200")
+    if a.workload == "weak":
+        strips = importlib.import_module("multigrid-petsc_b200.strips")
+        return strips.bench_weak(a, ClockSampler, hbm_peak)
     if world > 1:
         from importlib import import_module
         strips = import_module("multigrid-petsc_b200.strips")
@@ -286,6 +289,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="strong", choices=["strong", "weak"],
+                    help="strong (default): 8193^2 split over the GPUs (BASELINE configs[3]); weak: 4096 x 4097 points per GPU (configs[4])")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no busy loop, one e2e solve, no CPU baseline")
     a = ap.parse_args()
     if a.impl == "reference":

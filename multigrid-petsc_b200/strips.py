@@ -197,3 +197,70 @@ def selfcheck(npts=1025, levels=10, expect_sha=None, expect_iters=None):
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
+
+
+def bench_weak(a, ClockSampler, hbm_peak, rows_per_gpu=4096, ncols=4097):
+    """BASELINE configs[4]: weak scaling, 4096 x 4097 grid points per GPU.  The reference forces square grids
+    (ref: src/poisson.c:73-75), so P = 2, 8 are not expressible through the host C layer; this goes through the
+    C-ABI engine directly with a rectangular (4096 P - 1) x 4095 grid of unknowns, operator 1/h^2 [1 1 -4 1 1] per
+    level as the reference's OpA gives on a uniform mesh, separable synthetic right-hand side."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = 0, int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        rank, world = init_distributed("nccl")
+    torch.cuda.set_device(local)
+    ni, nj = rows_per_gpu * world - 1, ncols - 2
+    levels = 1
+    while ((nj + 1) >> levels) - 1 >= 1 and ((ni + 1) >> levels) - 1 >= 1:
+        levels += 1
+    e = _pkg.Engine(levels, ni, nj, device=local, rank=rank, nranks=world)
+    e.set_poisson_uniform()
+    if world > 1:
+        connect(e)
+    y = np.linspace(0.0, 1.0, ni + 2)[1:-1]
+    x = np.linspace(0.0, 1.0, nj + 2)[1:-1]
+    e.set_rhs_separable(-2 * np.pi ** 2 * np.sin(np.pi * x), np.sin(np.pi * y))
+    sm = _pkg.jacobi(0.8)
+    steps, warm = a.steps, max(a.warmup, 3)
+    e.solve_vcycle(sm, 3, 3, max_iter=warm, rtol=0.0)
+    l0 = e.launch_count()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    it, rn, _ = e.solve_vcycle(sm, 3, 3, max_iter=steps, rtol=0.0)
+    torch.cuda.synchronize()
+    ms = e.last_solve_ms()
+    launches = e.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+        ms = _max_over_ranks(ms)
+        launches = _sum_over_ranks(launches)
+    for _ in range(0 if a.profile else 6):
+        e.solve_vcycle(sm, 3, 3, max_iter=steps, rtol=0.0)
+    clocks = clk.stop() if rank == 0 else None
+    unknowns = float(ni) * nj
+    value = steps / (ms * 1e-3)
+    peak, peak_kind = hbm_peak()
+    e.close()
+    if rank == 0:
+        line = {"metric": "V-cycles/sec (fp64, weak scaling 4096 x 4097 points per GPU)", "value": value, "unit": "V-cycles/s",
+                "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"2D Poisson {ni + 2} x {nj + 2} fp64 (4096 rows per GPU), {levels}-level V(3,3), Richardson+Jacobi 0.8 "
+                           "(BASELINE configs[4])", "unknowns": unknowns, "l2": "inputs larger than L2 (134 MB per strip vector)",
+                           "parallelism": f"{world} row strips"},
+                "clocks": clocks, "unknown_updates_per_s": unknowns * value,
+                "roofline": {"bound": "hbm", "kernel": "whole V-cycle, unfused SURVEY 8d count (264 B per fine unknown)",
+                             "achieved": 264.0 * unknowns * value / 1e9, "peak": peak * world, "unit": "GB/s",
+                             "frac": 264.0 * unknowns * value / 1e9 / (peak * world), "peak_kind": peak_kind + f" x {world} GPUs", "traffic": None},
+                "gpu_launches": int(launches), "final_relative_residual": float(rn[-1])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0

@@ -665,6 +665,7 @@ static int allreduce(mgb_engine *e, int nvals, int slot, int take_sqrt)
 // ------------------------------------------------------------------------------------------------ CSR (single rank)
 static int alloc_csr(Csr &c, int m, int n, long long nnz)
 {
+	if (c.rowptr && c.m == m && c.n == n && c.nnz == nnz) return MGB_OK;   // re-assembly into the same arrays
 	free_csr(c);
 	if (nnz > 2147483647LL) return fail(MGB_EINVAL, "nnz %lld overflows the 32-bit PetscInt of the reference", nnz);
 	c.m = m; c.n = n; c.nnz = nnz;

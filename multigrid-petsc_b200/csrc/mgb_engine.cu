@@ -1163,7 +1163,7 @@ static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cud
 static int pick_rows(const LevelGeom &g, int ni)
 {
 	const int tiles = cdiv(g.pitch, FJ_VALID);
-	int chunks = 592 / tiles;
+	int chunks = (148 * (512 / FJ_THREADS)) / tiles;      // resident blocks: 512 threads per SM
 	if (chunks < 1) chunks = 1;
 	int r = cdiv(ni, chunks);
 	if (r < 16) r = 16;

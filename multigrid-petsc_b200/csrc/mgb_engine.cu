@@ -136,7 +136,7 @@ struct mgb_engine {
 	bool csr_built = false;
 	std::vector<struct GraphEntry> gcache;   // instantiated V-cycle graphs, keyed by parameters + pointer state
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
-	int coarse_threshold = 255;              // levels with at most this many rows run in the persistent bottom kernel
+	int coarse_threshold = 127;              // levels with at most this many rows run in the persistent bottom kernel
 	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)

@@ -107,6 +107,7 @@ struct JfState {
 	double2 win[D + 1][4];   // win[s][row & 3]: stage s of that row (rows t-s-2 .. t-s live)
 	double2 bq[4];           // b of rows t-4 .. t-1
 	double rw[4][3];         // POST_RESTRICT: residual row (own .x, own .y, east neighbour)
+	double wer[2];           // POST_*: west / east neighbours (stage D) of the row whose residual is formed at the NEXT step
 	double2 cq[3];           // PRE_PROLONG*: coarse rows T-1, T, T+1 (columns J0-1, J0) of the current group of four fine rows
 	double2 cn[2];           //               coarse rows T+2, T+3 requested for the next group
 	double acc;
@@ -166,6 +167,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	cp_async_wait<FJ_PF>();
 	double2 u0 = make_double2(0.0, 0.0);
 	if (PRE != PRE_ZERO) u0 = *reinterpret_cast<const double2 *>(&in_u[t & (FJ_NR - 1)][2 * tid]);
+	const double2 bold = S.bq[(K + 3) & 3];               // b of row t-5, evicted now (the residual of a D = 3 leg still needs it)
 	S.bq[(K + 3) & 3] = *reinterpret_cast<const double2 *>(&in_b[(t - 1) & (FJ_NR - 1)][2 * tid]);   // slot of row t-1
 	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
 		// t = 4m + K: coarse rows T-1, T, T+1 with T = 2m are in cq[0..2] (fine rows t..t+3 of the group need exactly these)
@@ -216,19 +218,19 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 		const int c = t - D;
 		if (B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
 	}
-	// ---- residual of row rho = t-D-1 from stage D
+	// ---- residual of row rho = t-D-2 from stage D.  It lags the stages by one more row so that all its inputs (rows
+	// rho-1 .. rho+1 of stage D and the neighbours of row rho, fetched during the previous step) predate this step:
+	// the residual is off the dependent chain stage 1 -> ... -> stage D of the step.
 	double2 res = make_double2(0.0, 0.0);
 	if (POST != POST_NONE) {
-		const int rho = t - D - 1;
+		const int rho = t - D - 2;
 		const int g = F.i0 + rho;
 		Coef cf = B.cu;
 		if (!UNI) cf = load_coef(F, A.gni, g);
-		const double2 xm = S.win[D][(K - D - 2) & 3], xc = S.win[D][(K - D - 1) & 3], xn = S.win[D][(K - D) & 3];
-		const double xw = shp[D][FJ_Y(tid - 1)];
-		const double xe = shp[D][FJ_X(tid + 1)];
-		const double2 bb = S.bq[(K - D - 1) & 3];
-		const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, xw, xc.x, xc.y, xn.x);
-		const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, xe, xn.y);
+		const double2 xm = S.win[D][(K - D - 3) & 3], xc = S.win[D][(K - D - 2) & 3], xn = S.win[D][(K - D - 1) & 3];
+		const double2 bb = (D + 2 <= 4) ? S.bq[(K - D - 2) & 3] : bold;
+		const double t0 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.x, S.wer[0], xc.x, xc.y, xn.x);
+		const double t1 = stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xm.y, xc.x, xc.y, S.wer[1], xn.y);
 		res.x = sub(bb.x, t0); res.y = sub(bb.y, t1);
 		if (MASK) {
 			const bool rok = g >= 0 && g < A.gni;
@@ -238,13 +240,16 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 		if (POST == POST_NORM) {
 			if (B.st_ok && rho >= B.y0 && rho < B.y1) S.acc += res.x * res.x + res.y * res.y;
 		}
+		// neighbours of stage D, row t-D-1 (published in the previous step): the centre row of the next step's residual
+		S.wer[0] = shp[D][FJ_Y(tid - 1)];
+		S.wer[1] = shp[D][FJ_X(tid + 1)];
 	}
 	// ---- restriction of the residual rows completed in the previous step (their east neighbours are visible now)
 	if (POST == POST_RESTRICT) {
-		constexpr int RP = (K - D - 2) & 3;               // slot of row rp = t-D-2
+		constexpr int RP = (K - D - 3) & 3;               // slot of row rp = t-D-3
 		S.rw[RP][2] = shp[D + 1][FJ_X(tid + 1)];          // column j0+2 of row rp
-		if ((((K - D - 2) & 1) == 0)) {
-			const int rp = t - D - 2;
+		if ((((K - D - 3) & 1) == 0)) {
+			const int rp = t - D - 3;
 			const int I = (rp >> 1) - 1;                   // coarse row (local) fed by fine rows rp-2 .. rp
 			const int J = B.j0 >> 1;
 			if (B.st_ok && I >= (B.y0 >> 1) && I < (B.y1 >> 1) && I < A.C.ni && J < A.C.pitch) {
@@ -261,7 +266,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 				A.bc[(size_t)I * A.C.pitch + J] = (J < A.C.nj) ? sum : 0.0;
 			}
 		}
-		S.rw[(K - D - 1) & 3][0] = res.x; S.rw[(K - D - 1) & 3][1] = res.y;
+		S.rw[(K - D - 2) & 3][0] = res.x; S.rw[(K - D - 2) & 3][1] = res.y;
 	}
 	// ---- publish the rows produced in this step
 #pragma unroll
@@ -281,7 +286,7 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 		for (int k = 0; k < 4; ++k) S.win[s][k] = make_double2(0.0, 0.0);
 #pragma unroll
 	for (int k = 0; k < 4; ++k) { S.bq[k] = make_double2(0.0, 0.0); S.rw[k][0] = 0.0; S.rw[k][1] = 0.0; S.rw[k][2] = 0.0; }
-	S.acc = 0.0;
+	S.acc = 0.0; S.wer[0] = 0.0; S.wer[1] = 0.0;
 	const LevelDev &F = A.F;
 	auto row_ok = [&](int i) {
 		if (!MASK) return true;
@@ -346,9 +351,9 @@ k_jfused(FusedArgs A)
 		B.cu.aS = vreg(c.aS); B.cu.aW = vreg(c.aW); B.cu.aC = vreg(c.aC); B.cu.aE = vreg(c.aE); B.cu.aN = vreg(c.aN);
 		B.cu.dinv = vreg(c.dinv); B.scale = vreg(A.scale);
 	}
-	// steps: stage 0 of row y0-D-1 is the first needed, the restriction of row y1 completes at step y1+D+2;
+	// steps: stage 0 of row y0-D-1 is the first needed, the restriction of row y1 completes at step y1+D+3;
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
-	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 2;
+	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 3;
 	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
 	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
 	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 4 + FJ_PF < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) &&

@@ -543,9 +543,8 @@ static int xfer_run(mgb_engine *e, std::vector<XferArgs> &args, const std::vecto
 // levels travel together, one flag, one wait).  Compute helpers flush the levels they read before launching, so e.g.
 // the ghost rows of u[l] written by the down leg travel together with those of u[l+1] right before the up leg of
 // level l, and a restricted right-hand side travels alone right before the next level's down leg.
-static void add_dst(XferArgs &a, const double *src, double *dst, unsigned long long cnt2, unsigned long long *peer_flag_base, int chan_dummy)
+static void add_dst(XferArgs &a, const double *src, double *dst, unsigned long long cnt2, unsigned long long *peer_flag_base)
 {
-	(void)chan_dummy;
 	const int d = a.ndst++;
 	a.src[d] = src; a.dst[d] = dst; a.cnt2[d] = cnt2; a.peer_flag[d] = peer_flag_base;   // flag base of the destination rank; channel offset added at flush
 }
@@ -601,17 +600,17 @@ static int flush_levels(mgb_engine *e, int lo, int hi)
 				const unsigned long long cnt2 = (unsigned long long)q.depth * pitch / 2;
 				const int ni = e->lay[r].ni[l];
 				if (r > 0) {                               // my first rows -> the lower ghost rows of rank r-1
-					add_dst(a, mine, peer_vec(e, r - 1, l, k) + (size_t)e->lay[r - 1].ni[l] * pitch, cnt2, flags_of(e, r - 1), 0);
+					add_dst(a, mine, peer_vec(e, r - 1, l, k) + (size_t)e->lay[r - 1].ni[l] * pitch, cnt2, flags_of(e, r - 1));
 					wait_mask |= 1u << (r - 1);
 				}
 				if (r < e->P - 1) {                        // my last rows -> the upper ghost rows of rank r+1
-					add_dst(a, mine + (size_t)(ni - q.depth) * pitch, peer_vec(e, r + 1, l, k) - (size_t)q.depth * pitch, cnt2, flags_of(e, r + 1), 0);
+					add_dst(a, mine + (size_t)(ni - q.depth) * pitch, peer_vec(e, r + 1, l, k) - (size_t)q.depth * pitch, cnt2, flags_of(e, r + 1));
 					wait_mask |= 1u << (r + 1);
 				}
 			} else if (q.type == REQ_GATHER) {
 				if (r != 0) {
 					const int c0 = e->geo[l].rows[r], c1 = e->geo[l].rows[r + 1];
-					add_dst(a, mine + (size_t)c0 * pitch, peer_vec(e, 0, l, k) + (size_t)c0 * pitch, (unsigned long long)(c1 - c0) * pitch / 2, flags_of(e, 0), 0);
+					add_dst(a, mine + (size_t)c0 * pitch, peer_vec(e, 0, l, k) + (size_t)c0 * pitch, (unsigned long long)(c1 - c0) * pitch / 2, flags_of(e, 0));
 				} else wait_mask |= ((1u << e->P) - 1u) & ~1u;
 			} else {
 				if (r == 0) {
@@ -619,7 +618,7 @@ static int flush_levels(mgb_engine *e, int lo, int hi)
 						int c0 = e->geo[l].rows[t] - 3, c1 = e->geo[l].rows[t + 1] + 3;   // the fused up leg reads 3 coarse ghost rows
 						if (c0 < 0) c0 = 0;
 						if (c1 > e->geo[l].gni) c1 = e->geo[l].gni;
-						add_dst(a, mine + (size_t)c0 * pitch, peer_vec(e, t, l, k) + (size_t)c0 * pitch, (unsigned long long)(c1 - c0) * pitch / 2, flags_of(e, t), 0);
+						add_dst(a, mine + (size_t)c0 * pitch, peer_vec(e, t, l, k) + (size_t)c0 * pitch, (unsigned long long)(c1 - c0) * pitch / 2, flags_of(e, t));
 					}
 				} else wait_mask |= 1u;
 			}

@@ -423,3 +423,30 @@ def test_solve_rhs_many_matches_single_solves(extra):
         assert us[2].tobytes() == singles[2][2].tobytes()
     finally:
         s.close()
+
+
+# ------------------------------------------------------------------ rectangular grids (the weak-scaling workload)
+@pytest.mark.parametrize("ni,nj,levels", [(383, 127, 6), (127, 255, 5), (767, 95, 4)])
+def test_rectangular_grid_paths_agree(ni, nj, levels):
+    """The reference forces square grids (src/poisson.c:73-75); bench.py --workload weak uses ni != nj through the
+    C-ABI.  No oracle there, so the three code paths are checked against each other bit for bit: one kernel per
+    sweep, fused legs + bottom kernel, and fused legs on 2 / 3 emulated strips."""
+    rng = np.random.default_rng(ni + nj)
+    b = rng.uniform(-1, 1, (ni, nj))
+    outs = []
+    for kw, solve_kw in ((dict(), dict(fuse=False)), (dict(), dict(fuse=True)), (dict(), dict(fuse=True, bottom=False)),
+                         (dict(nranks=2, emulate=True, agglomerate_below=63), dict(fuse=True)),
+                         (dict(nranks=3, emulate=True, agglomerate_below=63), dict(fuse=False))):
+        e = mgb.Engine(levels, ni, nj, **kw)
+        try:
+            e.set_poisson_uniform()
+            e.set_vec(mgb.VEC_B, 0, b)
+            it, rn, _ = e.solve_vcycle(mgb.jacobi(0.8), 3, 3, max_iter=12, rtol=1e-7, **solve_kw)
+            outs.append((it, rn, e.get_vec(mgb.VEC_U, 0)))
+        finally:
+            e.close()
+    for it, rn, u in outs[1:]:
+        assert it == outs[0][0]
+        assert u.tobytes() == outs[0][2].tobytes()
+        assert np.allclose(rn, outs[0][1], rtol=1e-12, atol=RNORM_ATOL)
+    assert outs[0][1][-1] < outs[0][1][0]

@@ -125,6 +125,11 @@ int  mgb_set_transfer(mgb_engine *e, const double res3[9], const double pro3[9])
 int  mgb_assemble_csr(mgb_engine *e);                     /* A[l] all levels, res[l], pro[l]        */
 int  mgb_csr_dims(const mgb_engine *e, int which, int level, int *m, int *n, long long *nnz);
 int  mgb_csr_get(const mgb_engine *e, int which, int level, int *rowptr, int *col, double *val);
+/* With row strips each rank assembles the rows it owns (local row pointers, GLOBAL column indices -- the local rows of
+ * the reference's MPIAIJ matrices, ref: src/solver.c:218,502).  rank = -1: the first strip held by this process;
+ * row0 = global number of the first local row. */
+int  mgb_csr_dims_rank(const mgb_engine *e, int rank, int which, int level, int *m, int *n, long long *nnz, int *row0);
+int  mgb_csr_get_rank(const mgb_engine *e, int rank, int which, int level, int *rowptr, int *col, double *val);
 /* y = M x with the assembled matrix (MatMult_SeqAIJ order: ascending columns from 0.0); host vectors */
 int  mgb_csr_spmv(mgb_engine *e, int which, int level, const double *x, double *y);
 /* same, on the engine's own level vectors (no host traffic): y_vec[lout] = M x_vec[lin] */

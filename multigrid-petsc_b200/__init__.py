@@ -226,13 +226,16 @@ class Engine:
     def assemble_csr(self):
         self._ck(self.L.mgb_assemble_csr(self.h))
 
-    def csr(self, which, l):
-        m, n, nnz = C.c_int(), C.c_int(), C.c_longlong()
-        self._ck(self.L.mgb_csr_dims(self.h, which, l, C.byref(m), C.byref(n), C.byref(nnz)))
+    def csr(self, which, l, rank=-1, with_row0=False):
+        """(shape, rowptr, col, val) of the rows rank `rank` holds (-1: first local strip; the whole matrix on one rank)"""
+        m, n, nnz, r0 = C.c_int(), C.c_int(), C.c_longlong(), C.c_int()
+        self._ck(self.L.mgb_csr_dims_rank(self.h, rank, which, l, C.byref(m), C.byref(n), C.byref(nnz), C.byref(r0)))
         ia = np.zeros(m.value + 1, dtype=np.int32)
         ja = np.zeros(nnz.value, dtype=np.int32)
         va = np.zeros(nnz.value)
-        self._ck(self.L.mgb_csr_get(self.h, which, l, _pd(ia), _pd(ja), _pd(va)))
+        self._ck(self.L.mgb_csr_get_rank(self.h, rank, which, l, _pd(ia), _pd(ja), _pd(va)))
+        if with_row0:
+            return (m.value, n.value), ia, ja, va, r0.value
         return (m.value, n.value), ia, ja, va
 
     def csr_spmv(self, which, l, x):

@@ -21,41 +21,45 @@ __device__ __forceinline__ long long rowptr5(int i, int j, int ni, int nj)
 	return 5 * row - dropS - dropN - dropW - dropE;
 }
 
+// Rows of the grid rows [i0, i0 + nloc) only (a rank's row range, like the local rows of a PETSc MPIAIJ matrix):
+// row pointers start at 0 for the first local row, column indices are global.
 __global__ void __launch_bounds__(256)
 k_csr_A(int *__restrict__ rowptr, int *__restrict__ col, double *__restrict__ val, int ni, int nj,
-        const double *__restrict__ coef)
+        const double *__restrict__ coef, int i0, int nloc)
 {
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
-	const int i = blockIdx.y;
+	const int il = blockIdx.y;
 	if (j >= nj) return;
+	const int i = i0 + il;
 	const int row = i * nj + j;
-	long long p = rowptr5(i, j, ni, nj);
-	rowptr[row] = (int)p;
+	const long long base = rowptr5(i0, 0, ni, nj);
+	long long p = rowptr5(i, j, ni, nj) - base;
+	rowptr[il * nj + j] = (int)p;
 	const double *c = coef + (size_t)i * MGB_COEF_STRIDE;
 	if (i > 0)      { col[p] = row - nj; val[p] = c[0]; ++p; }
 	if (j > 0)      { col[p] = row - 1;  val[p] = c[1]; ++p; }
 	                { col[p] = row;      val[p] = c[2]; ++p; }
 	if (j < nj - 1) { col[p] = row + 1;  val[p] = c[3]; ++p; }
 	if (i < ni - 1) { col[p] = row + nj; val[p] = c[4]; ++p; }
-	if (i == ni - 1 && j == nj - 1) rowptr[row + 1] = (int)p;
+	if (il == nloc - 1 && j == nj - 1) rowptr[il * nj + j + 1] = (int)p;
 }
 
 // res[l]: coarse row (I,J) -> 9 entries at fine (2I+a, 2J+b), ascending (ref: src/solver.c:1078-1088)
 __global__ void __launch_bounds__(256)
-k_csr_R(int *__restrict__ rowptr, int *__restrict__ col, double *__restrict__ val, int nci, int ncj, int nfj, Stencil3 R)
+k_csr_R(int *__restrict__ rowptr, int *__restrict__ col, double *__restrict__ val, int nci, int ncj, int nfj, Stencil3 R, int I0)
 {
 	const int J = blockIdx.x * blockDim.x + threadIdx.x;
-	const int I = blockIdx.y;
+	const int Il = blockIdx.y;                       // local coarse grid row; nci = local coarse rows, I0 = first global one
 	if (J >= ncj) return;
-	const int row = I * ncj + J;
+	const int row = Il * ncj + J;
 	const long long p = 9LL * row;
 	rowptr[row] = (int)p;
-	if (I == nci - 1 && J == ncj - 1) rowptr[row + 1] = (int)(p + 9);
+	if (Il == nci - 1 && J == ncj - 1) rowptr[row + 1] = (int)(p + 9);
 #pragma unroll
 	for (int a = 0; a < 3; ++a)
 #pragma unroll
 		for (int b = 0; b < 3; ++b) {
-			col[p + a * 3 + b] = (2 * I + a) * nfj + 2 * J + b;
+			col[p + a * 3 + b] = (2 * (I0 + Il) + a) * nfj + 2 * J + b;
 			val[p + a * 3 + b] = R.w[a * 3 + b];
 		}
 }
@@ -81,14 +85,16 @@ __device__ __forceinline__ long long touch_prefix(int t, int nc)
 // pro[l]: fine row (i,j) gets p[a][b] from coarse (I,J) with i = 2I+a, j = 2J+b (transpose pattern of res;
 // ref: src/solver.c:1138-1148), entries in ascending coarse column order.
 __global__ void __launch_bounds__(256)
-k_csr_P(int *__restrict__ rowptr, int *__restrict__ col, double *__restrict__ val, int nfi, int nfj, int nci, int ncj, Stencil3 Pw)
+k_csr_P(int *__restrict__ rowptr, int *__restrict__ col, double *__restrict__ val, int nfi, int nfj, int nci, int ncj, Stencil3 Pw,
+        int i0, int nloc)
 {
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
-	const int i = blockIdx.y;
+	const int il = blockIdx.y;                       // local fine grid row of the rows [i0, i0 + nloc); nfi, nci are global
 	if (j >= nfj) return;
-	const int row = i * nfj + j;
+	const int i = i0 + il;
+	const int row = il * nfj + j;
 	const long long rowsum = touch_prefix(nfj, ncj);             // entries per unit of touch_count(i)
-	long long p = touch_prefix(i, nci) * rowsum + (long long)touch_count(i, nci) * touch_prefix(j, ncj);
+	long long p = (touch_prefix(i, nci) - touch_prefix(i0, nci)) * rowsum + (long long)touch_count(i, nci) * touch_prefix(j, ncj);
 	rowptr[row] = (int)p;
 	const int Ilo = (i & 1) ? (i - 1) / 2 : i / 2 - 1, Ihi = (i & 1) ? Ilo : i / 2;
 	const int Jlo = (j & 1) ? (j - 1) / 2 : j / 2 - 1, Jhi = (j & 1) ? Jlo : j / 2;
@@ -101,7 +107,7 @@ k_csr_P(int *__restrict__ rowptr, int *__restrict__ col, double *__restrict__ va
 			++p;
 		}
 	}
-	if (i == nfi - 1 && j == nfj - 1) rowptr[row + 1] = (int)p;
+	if (il == nloc - 1 && j == nfj - 1) rowptr[row + 1] = (int)p;
 }
 
 // y = M x, one thread per row, ascending columns, accumulation from 0.0 (MatMult_SeqAIJ).

@@ -681,70 +681,101 @@ static long long host_touch_prefix(int t, int nc)
 	return s;
 }
 
+// A[l], res[l], pro[l] in CSR.  With row strips every rank assembles the rows it owns -- the grid rows of its strip for
+// A and pro, its coarse rows for res -- with local row pointers and GLOBAL column indices, i.e. the local rows of the
+// reference's MPIAIJ matrices (ref: src/solver.c:218 "for row in [ranges[rank], ranges[rank+1])", :502); agglomerated
+// levels are assembled whole on rank 0.
 extern "C" int mgb_assemble_csr(mgb_engine *e)
 {
 	TRY(require_ops(e, true));
 	if (e->cfg.red_black_numbering)
 		return fail(MGB_EINVAL, "CSR assembly is offered for the reference's natural numbering only (-map 0,1,2), not the -map 3 extension");
-	if (e->P > 1) return fail(MGB_EINVAL, "CSR assembly runs on a single rank (the strips solve matrix-free)");
-	Strip &s = e->strips[0];
-	for (int l = 0; l < e->L; ++l) {
-		SLevel &S = s.lev[l]; const LevelGeom &g = e->geo[l];
-		const long long N = (long long)g.gni * g.nj;
-		if (N > 2147483647LL) return fail(MGB_EINVAL, "level %d has more rows than a 32-bit PetscInt holds", l);
-		const long long nnz = 5 * N - 2LL * g.gni - 2LL * g.nj;
-		TRY(alloc_csr(S.A, (int)N, (int)N, nnz));
-		dim3 gr(cdiv(g.nj, 256), g.gni);
-		k_csr_A<<<gr, 256, 0, s.stream>>>(S.A.rowptr, S.A.col, S.A.val, g.gni, g.nj, S.coef);
-		LAUNCHED(e); KCHECK();
-		if (l + 1 < e->L) {
-			const LevelGeom &c = e->geo[l + 1];
-			const long long NC = (long long)c.gni * c.nj;
-			TRY(alloc_csr(S.R, (int)NC, (int)N, 9 * NC));
-			dim3 grr(cdiv(c.nj, 256), c.gni);
-			k_csr_R<<<grr, 256, 0, s.stream>>>(S.R.rowptr, S.R.col, S.R.val, c.gni, c.nj, g.nj, e->R3);
+	for (auto &s : e->strips) {
+		const int r = s.rank;
+		for (int l = 0; l < e->L; ++l) {
+			SLevel &S = s.lev[l]; const LevelGeom &g = e->geo[l];
+			if (!(S.present && S.active)) continue;
+			const long long NG = (long long)g.gni * g.nj;
+			if (NG > 2147483647LL) return fail(MGB_EINVAL, "level %d has more rows than a 32-bit PetscInt holds", l);
+			const int i0 = S.r0, nloc = S.ni;
+			const long long N = (long long)nloc * g.nj;
+			// entries of the local rows: 5 per row minus the dropped neighbours (first / last grid row, first / last column)
+			const long long nnz = 5 * N - 2LL * nloc - (i0 == 0 ? g.nj : 0) - (i0 + nloc == g.gni ? g.nj : 0);
+			TRY(alloc_csr(S.A, (int)N, (int)NG, nnz));
+			dim3 gr(cdiv(g.nj, 256), nloc);
+			k_csr_A<<<gr, 256, 0, s.stream>>>(S.A.rowptr, S.A.col, S.A.val, g.gni, g.nj, S.coef, i0, nloc);
 			LAUNCHED(e); KCHECK();
-			const long long pnnz = host_touch_prefix(g.gni, c.gni) * host_touch_prefix(g.nj, c.nj);
-			TRY(alloc_csr(S.P, (int)N, (int)NC, pnnz));
-			k_csr_P<<<gr, 256, 0, s.stream>>>(S.P.rowptr, S.P.col, S.P.val, g.gni, g.nj, c.gni, c.nj, e->P3);
-			LAUNCHED(e); KCHECK();
+			if (l + 1 < e->L) {
+				const LevelGeom &c = e->geo[l + 1];
+				// coarse rows this rank produces in the restriction from level l
+				int I0 = 0, ncl = c.gni;
+				if (g.dist) { I0 = c.rows[r]; ncl = c.rows[r + 1] - c.rows[r]; }
+				const long long NC = (long long)ncl * c.nj;
+				TRY(alloc_csr(S.R, (int)NC, (int)NG, 9 * NC));
+				if (ncl > 0) {
+					dim3 grr(cdiv(c.nj, 256), ncl);
+					k_csr_R<<<grr, 256, 0, s.stream>>>(S.R.rowptr, S.R.col, S.R.val, ncl, c.nj, g.nj, e->R3, I0);
+					LAUNCHED(e); KCHECK();
+				}
+				const long long pnnz = (host_touch_prefix(i0 + nloc, c.gni) - host_touch_prefix(i0, c.gni)) * host_touch_prefix(g.nj, c.nj);
+				TRY(alloc_csr(S.P, (int)N, (int)((long long)c.gni * c.nj), pnnz));
+				k_csr_P<<<gr, 256, 0, s.stream>>>(S.P.rowptr, S.P.col, S.P.val, g.gni, g.nj, c.gni, c.nj, e->P3, i0, nloc);
+				LAUNCHED(e); KCHECK();
+			}
 		}
+		CU(cudaStreamSynchronize(s.stream));
 	}
-	CU(cudaStreamSynchronize(s.stream));
 	e->csr_built = true;
 	return MGB_OK;
 }
 
-static int pick_csr(const mgb_engine *e, int which, int level, const Csr **out)
+// matrix `which` of level `level` as held by rank `rank` (-1: the first local strip)
+static int pick_csr(const mgb_engine *e, int rank, int which, int level, const Csr **out, int *row0)
 {
 	if (!e) return fail(MGB_EINVAL, "null engine");
 	if (!e->csr_built) return fail(MGB_ESTATE, "mgb_assemble_csr was not called");
 	if (level < 0 || level >= e->L) return fail(MGB_EINVAL, "level %d out of range", level);
-	const SLevel &S = e->strips[0].lev[level];
+	const Strip *sp = &e->strips[0];
+	if (rank >= 0) {
+		sp = nullptr;
+		for (auto &s : e->strips) if (s.rank == rank) sp = &s;
+		if (!sp) return fail(MGB_EINVAL, "rank %d is not held by this process", rank);
+	}
+	const SLevel &S = sp->lev[level];
+	if (!(S.present && S.active)) return fail(MGB_EINVAL, "rank %d holds no rows of level %d", sp->rank, level);
+	int r0 = S.r0 * e->geo[level].nj;
 	if (which == MGB_MAT_A) *out = &S.A;
 	else if (level + 1 >= e->L) return fail(MGB_EINVAL, "no transfer operator below the coarsest level");
-	else if (which == MGB_MAT_RES) *out = &S.R;
+	else if (which == MGB_MAT_RES) { *out = &S.R; r0 = (e->geo[level].dist ? e->geo[level + 1].rows[sp->rank] : 0) * e->geo[level + 1].nj; }
 	else if (which == MGB_MAT_PRO) *out = &S.P;
 	else return fail(MGB_EINVAL, "matrix id %d out of range", which);
+	if (row0) *row0 = r0;
 	return MGB_OK;
 }
 
-extern "C" int mgb_csr_dims(const mgb_engine *e, int which, int level, int *m, int *n, long long *nnz)
+extern "C" int mgb_csr_dims_rank(const mgb_engine *e, int rank, int which, int level, int *m, int *n, long long *nnz, int *row0)
 {
-	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, rank, which, level, &c, row0));
 	if (m) *m = c->m;
 	if (n) *n = c->n;
 	if (nnz) *nnz = c->nnz;
 	return MGB_OK;
 }
-
+extern "C" int mgb_csr_get_rank(const mgb_engine *e, int rank, int which, int level, int *rowptr, int *col, double *val)
+{
+	const Csr *c = nullptr; TRY(pick_csr(e, rank, which, level, &c, nullptr));
+	if (rowptr) CU(cudaMemcpy(rowptr, c->rowptr, sizeof(int) * ((size_t)c->m + 1), cudaMemcpyDeviceToHost));
+	if (col && c->nnz) CU(cudaMemcpy(col, c->col, sizeof(int) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
+	if (val && c->nnz) CU(cudaMemcpy(val, c->val, sizeof(double) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
+	return MGB_OK;
+}
+extern "C" int mgb_csr_dims(const mgb_engine *e, int which, int level, int *m, int *n, long long *nnz)
+{
+	return mgb_csr_dims_rank(e, -1, which, level, m, n, nnz, nullptr);
+}
 extern "C" int mgb_csr_get(const mgb_engine *e, int which, int level, int *rowptr, int *col, double *val)
 {
-	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
-	if (rowptr) CU(cudaMemcpy(rowptr, c->rowptr, sizeof(int) * ((size_t)c->m + 1), cudaMemcpyDeviceToHost));
-	if (col) CU(cudaMemcpy(col, c->col, sizeof(int) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
-	if (val) CU(cudaMemcpy(val, c->val, sizeof(double) * (size_t)c->nnz, cudaMemcpyDeviceToHost));
-	return MGB_OK;
+	return mgb_csr_get_rank(e, -1, which, level, rowptr, col, val);
 }
 
 // ------------------------------------------------------------------------------------------------ vectors
@@ -1381,7 +1412,8 @@ static int csr_spmv_dev(mgb_engine *e, const Csr *c, const double *x, int xn, in
 }
 extern "C" int mgb_csr_spmv_vec(mgb_engine *e, int which, int level, int x_vec, int y_vec)
 {
-	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, -1, which, level, &c, nullptr));
+	if (e->P > 1) return fail(MGB_EINVAL, "CSR SpMV runs on a single rank (strips apply the operator matrix-free)");
 	const int lx = (which == MGB_MAT_PRO) ? level + 1 : level;
 	const int ly = (which == MGB_MAT_RES) ? level + 1 : level;
 	if (lx == ly && x_vec == y_vec) return fail(MGB_EINVAL, "x and y must differ");
@@ -1392,7 +1424,8 @@ extern "C" int mgb_csr_spmv_vec(mgb_engine *e, int which, int level, int x_vec, 
 }
 extern "C" int mgb_csr_spmv(mgb_engine *e, int which, int level, const double *x, double *y)
 {
-	const Csr *c = nullptr; TRY(pick_csr(e, which, level, &c));
+	const Csr *c = nullptr; TRY(pick_csr(e, -1, which, level, &c, nullptr));
+	if (e->P > 1) return fail(MGB_EINVAL, "CSR SpMV runs on a single rank (strips apply the operator matrix-free)");
 	if (!x || !y) return fail(MGB_EINVAL, "null argument");
 	cudaStream_t st = e->strips[0].stream;
 	double *dx, *dy;

@@ -113,7 +113,6 @@ void Assemble(Problem *prob, Mesh *mesh, Indices *indices, Operator *op, Solver 
 	pbopt_get_int("-mgb_agglomerate", &cfg.agglomerate_below);
 	pbopt_get_int("-mgb_emulate", &cfg.emulate);
 	pbopt_get_int("-mgb_device", &cfg.device);
-	if (cfg.nranks > 1) want_csr = 0;
 	mgb_engine *e = NULL;
 	if (mgb_create(&cfg, &e) != MGB_OK) die("mgb_create");
 	set_engine(assem, e);

@@ -450,3 +450,35 @@ def test_rectangular_grid_paths_agree(ni, nj, levels):
         assert u.tobytes() == outs[0][2].tobytes()
         assert np.allclose(rn, outs[0][1], rtol=1e-12, atol=RNORM_ATOL)
     assert outs[0][1][-1] < outs[0][1][0]
+
+
+# ------------------------------------------------------------------ CSR assembly on row strips
+@pytest.mark.parametrize("ranks,aggl", [(2, 31), (3, 31), (4, 31), (2, 15)])
+def test_csr_on_strips_concatenates_to_the_reference_matrix(ranks, aggl):
+    """Every rank assembles the rows it owns (local row pointers, global columns): stacked in rank order they must be
+    the oracle's matrix, bit for bit -- for A, res and pro on every level."""
+    opts = base(129, 5) + " " + JAC
+    o = Oracle(opts)
+    e = mgb.Engine(5, 127, nranks=ranks, emulate=True, agglomerate_below=aggl)
+    try:
+        e.set_poisson_uniform()
+        e.assemble_csr()
+        for l in range(5):
+            for which in (mgb.MAT_A, mgb.MAT_RES, mgb.MAT_PRO):
+                if which != mgb.MAT_A and l == 4:
+                    continue
+                shape_o, ia_o, ja_o, va_o = o.csr(which, l)
+                dist = mgb.strip_rows(5, 127, 127, ranks, l, 0, aggl)[2]
+                ia, ja, va, rows = [np.zeros(1, dtype=np.int64)], [], [], 0
+                for r in (range(ranks) if dist else [0]):
+                    (m, n), ia_r, ja_r, va_r, row0 = e.csr(which, l, rank=r, with_row0=True)
+                    assert n == shape_o[1] and row0 == rows
+                    ia.append(ia_r[1:].astype(np.int64) + ia[-1][-1])
+                    ja.append(ja_r); va.append(va_r); rows += m
+                assert rows == shape_o[0]
+                assert np.array_equal(np.concatenate(ia), ia_o)
+                assert np.array_equal(np.concatenate(ja), ja_o)
+                assert np.concatenate(va).tobytes() == va_o.tobytes()
+    finally:
+        e.close()
+        o.close()

@@ -168,7 +168,7 @@ typedef struct {
 	int    use_graph;       /* 1: replay the cycle as a CUDA graph (same kernels, same order)    */
 	int    no_fuse;         /* 1: one kernel per sweep / transfer (default 0: each leg of a level in one pass,
 	                           csrc/mgb_fused.cuh -- same arithmetic per value, bit-identical results)          */
-	int    no_bottom;       /* 1: do not run the levels with <= 127 rows as one persistent cluster launch
+	int    no_bottom;       /* 1: do not run the levels with <= 63 rows as one persistent cluster launch
 	                           (csrc/mgb_coarse_cycle.cuh); only meaningful with the fused legs                 */
 } mgb_vcycle_params;
 

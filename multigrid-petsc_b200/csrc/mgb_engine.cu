@@ -136,7 +136,7 @@ struct mgb_engine {
 	bool csr_built = false;
 	std::vector<struct GraphEntry> gcache;   // instantiated V-cycle graphs, keyed by parameters + pointer state
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
-	int coarse_threshold = 127;              // levels with at most this many rows run in the persistent bottom kernel
+	int coarse_threshold = 63;               // levels with at most this many rows run in the persistent bottom kernel
 	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
@@ -1189,14 +1189,14 @@ static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cud
 
 // rows per block of the fused kernel.  The kernel runs 4 blocks per SM (registers and shared memory): 592 resident
 // blocks on 148 SMs.  Large levels get exactly one wave (no partially filled second wave), i.e. as many row chunks as
-// fit next to the column tiles; small levels get chunks of at least 16 rows.
+// fit next to the column tiles; small levels get chunks of at least 4 rows (the row loop of a block is a serial chain: short chunks, many blocks).
 static int pick_rows(const LevelGeom &g, int ni)
 {
 	const int tiles = cdiv(g.pitch, FJ_VALID);
 	int chunks = (148 * (512 / FJ_THREADS)) / tiles;      // resident blocks: 512 threads per SM
 	if (chunks < 1) chunks = 1;
 	int r = cdiv(ni, chunks);
-	if (r < 16) r = 16;
+	if (r < 4) r = 4;
 	return (r + 1) & ~1;
 }
 

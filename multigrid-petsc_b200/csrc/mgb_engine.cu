@@ -1126,10 +1126,17 @@ static LevelDev coarse_view(const mgb_engine *e, const Strip &s, int lc, bool fi
 // b[l+1] = res[l] * (fused ? bv[l] - A[l] xv[l] : rv[l])   (ref: src/solver.c:1534-1535).  Every strip of a
 // distributed level produces its own coarse rows; when the coarse level is the first agglomerated one they are
 // gathered on rank 0, otherwise the coarse ghost rows are exchanged.  Needs ghost depth 2 of xv and 1 of bv / rv.
+static int restrict_streamed(mgb_engine *e, int l, int bv, int xv);
 static int restrict_to_coarse(mgb_engine *e, int l, int bv, int xv, int rv, bool fused)
 {
 	TRY(flush_levels(e, l, l));
 	const LevelGeom &gf = e->geo[l], &gc = e->geo[l + 1];
+	if (fused && !e->cfg.red_black_numbering) {
+		TRY(restrict_streamed(e, l, bv, xv));
+		if (gc.dist) return halo(e, l + 1, MGB_VEC_B, 2);
+		if (gf.dist) return gather_rows(e, l + 1, MGB_VEC_B);
+		return MGB_OK;
+	}
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
 		SLevel &F = s.lev[l], &C = s.lev[l + 1];
@@ -1198,6 +1205,31 @@ static int pick_rows(const LevelGeom &g, int ni)
 	int r = cdiv(ni, chunks);
 	if (r < 4) r = 4;
 	return (r + 1) & ~1;
+}
+
+// b[l+1] = res[l] * (b - A x) as a streaming pass (the fused kernel with zero sweeps): natural numbering only
+static int restrict_streamed(mgb_engine *e, int l, int bv, int xv)
+{
+	const LevelGeom &g = e->geo[l];
+	TRY(flush_levels(e, l, l));
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		FusedArgs a; memset(&a, 0, sizeof a);
+		a.u_in = S.v[xv]; a.b = S.v[bv]; a.u_out = nullptr;
+		a.F = ldev(e, s, l); a.scale = 1.0; a.gni = g.gni;
+		a.rows = pick_rows(g, S.ni);
+		a.R3 = e->R3; a.P3 = e->P3;
+		size_t coff; a.C = coarse_view(e, s, l + 1, g.dist, &coff);
+		a.bc = s.lev[l + 1].v[MGB_VEC_B] + coff;
+		int tiles = cdiv(g.pitch, FJ_VALID);
+		const int need = cdiv(2 * e->geo[l + 1].pitch, FJ_VALID);
+		if (need > tiles) tiles = need;
+		dim3 grid(tiles, cdiv(S.ni, a.rows));
+		launch_jfused<0, PRE_GIVEN, POST_RESTRICT>(a, grid, s.stream);
+		LAUNCHED(e); KCHECK();
+	}
+	return MGB_OK;
 }
 
 static bool fusable(const mgb_engine *e, const mgb_smoother *sm) { return sm->type == MGB_SMOOTH_JACOBI && !e->cfg.red_black_numbering; }

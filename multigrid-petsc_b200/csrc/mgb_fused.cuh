@@ -216,7 +216,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	// ---- the finished row t-D
 	{
 		const int c = t - D;
-		if (B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
+		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);   // D = 0: u is unchanged
 	}
 	// ---- residual of row rho = t-D-2 from stage D.  It lags the stages by one more row so that all its inputs (rows
 	// rho-1 .. rho+1 of stage D and the neighbours of row rho, fetched during the previous step) predate this step:

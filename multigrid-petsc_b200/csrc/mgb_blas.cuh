@@ -136,3 +136,24 @@ __global__ void k_publish(double *__restrict__ host_mapped, const double *__rest
 	if ((int)threadIdx.x < count) host_mapped[first + threadIdx.x] = dev[first + threadIdx.x];
 	__threadfence_system();
 }
+
+// The CG vector update in one pass (KSPSolve_CG: VecAXPY(x, a, p); VecAXPY(r, -a, w); VecNorm(r)):
+// x += a p ; r -= a w ; partial[block] = sum r^2.  40 B per unknown instead of 24 + 24 + 8.
+__global__ void __launch_bounds__(MGB_RED_THREADS)
+k_cg_update(double *__restrict__ x, const double *__restrict__ p, double *__restrict__ r, const double *__restrict__ w,
+            size_t n2, double a, double *__restrict__ partial)
+{
+	double acc = 0.0;
+	const double ma = -a;
+	const size_t stride = (size_t)gridDim.x * MGB_RED_THREADS;
+	for (size_t k = (size_t)blockIdx.x * MGB_RED_THREADS + threadIdx.x; k < n2; k += stride) {
+		const double2 xv = ld2(x + 2 * k), pv = ld2(p + 2 * k), rv = ld2(r + 2 * k), wv = ld2(w + 2 * k);
+		double2 xo, ro;
+		xo.x = add(xv.x, mul(a, pv.x)); xo.y = add(xv.y, mul(a, pv.y));
+		ro.x = add(rv.x, mul(ma, wv.x)); ro.y = add(rv.y, mul(ma, wv.y));
+		st2(x + 2 * k, xo); st2(r + 2 * k, ro);
+		acc += ro.x * ro.x + ro.y * ro.y;
+	}
+	const double s = block_sum<MGB_RED_THREADS>(acc);
+	if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}

@@ -998,6 +998,41 @@ static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha)
 	}
 	return MGB_OK;
 }
+// y = A x ; scal[slot] = x . y in one pass (the w = A p, p'w pair of CG)
+static int k_apply_dot(mgb_engine *e, int l, int xv, int yv, int slot)
+{
+	TRY(flush_levels(e, l, l));
+	const LevelGeom &g = e->geo[l];
+	std::vector<int> nb;
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const int ry = pick_ry(g, S.ni);
+		const dim3 gr = stream_grid(g, S.ni, ry);
+		if ((size_t)gr.x * gr.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
+		k_stream5<ST_APPLYDOT><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], nullptr, S.v[yv], ldev(e, s, l), 0.0, s.partial, ry);
+		LAUNCHED(e); KCHECK();
+		nb.push_back((int)(gr.x * gr.y));
+	}
+	return reduce_tail(e, l, nb, slot, 0);
+}
+// x += a p ; r -= a w ; scal[slot] = ||r||_2 in one pass (the CG update, mgb_blas.cuh: k_cg_update)
+static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, double a, int slot)
+{
+	const LevelGeom &g = e->geo[l];
+	std::vector<int> nb;
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const size_t n2 = (size_t)S.ni * g.pitch / 2;
+		size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
+		const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
+		k_cg_update<<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial);
+		LAUNCHED(e); KCHECK();
+		nb.push_back(blocks);
+	}
+	return reduce_tail(e, l, nb, slot, 1);
+}
 // scal[first .. first+count) of the first local strip -> its pinned mirror (every rank holds identical values)
 static int read_scalars(mgb_engine *e, int first, int count)
 {
@@ -1793,14 +1828,13 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 				else { TRY(k_vecop<1>(e, 0, Pv, Z, beta / betaold)); }                             // p = z + b p
 				dpiold = dpi;
 				TRY(halo(e, 0, Pv, 2));
-				TRY(k_apply(e, 0, Pv, Q));                                                         // w = A p
-				TRY(k_reduce(e, 0, Pv, Q, 0, 0)); TRY(read_scalars(e, 0, 1)); dpi = hs[0];
+				TRY(k_apply_dot(e, 0, Pv, Q, 0));                                                  // w = A p ; dpi = p'w
+				TRY(read_scalars(e, 0, 1)); dpi = hs[0];
 				betaold = beta;
 				if (dpi == 0.0 || (i > 0 && dpi * dpiold <= 0.0)) { reason = -10; break; }         // KSP_DIVERGED_INDEFINITE_MAT
 				const double a = beta / dpi;
-				TRY(k_vecop<0>(e, 0, X, Pv, a));                                                   // x = x + a p
-				TRY(k_vecop<0>(e, 0, R, Q, -a));                                                   // r = r - a w
-				TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
+				TRY(k_cg_step(e, 0, X, Pv, R, Q, a, 0));                                           // x = x + a p ; r = r - a w ; ||r||
+				TRY(read_scalars(e, 0, 1)); dp = hs[0];
 				logr(dp);
 				reason = ksp_converged(p, i + 1, dp, &rnorm0, &ttol);
 				if (reason) break;

@@ -11,7 +11,7 @@
 #define MGB_SB_THREADS 128          // threads per block of the streaming kernels
 #define MGB_SB_COLS (2 * MGB_SB_THREADS)
 
-enum { ST_APPLY = 0, ST_RESID = 1, ST_RESNORM = 2, ST_JACOBI = 3 };
+enum { ST_APPLY = 0, ST_RESID = 1, ST_RESNORM = 2, ST_JACOBI = 3, ST_APPLYDOT = 4 };   // APPLYDOT: y = A x and partial sums of x . y (CG)
 
 // x: input vector, b: right-hand side (unused for ST_APPLY), y: output (unused for ST_RESNORM)
 // partial: one double per block (ST_RESNORM)
@@ -38,7 +38,7 @@ k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__
 			const double2 xn = ld2(xp + P);
 			const double xnw = xp[P - 1], xne = xp[P + 2];
 			double2 bb = make_double2(0.0, 0.0);
-			if (MODE != ST_APPLY) bb = ld2(b + (size_t)i * P + j0);
+			if (MODE != ST_APPLY && MODE != ST_APPLYDOT) bb = ld2(b + (size_t)i * P + j0);
 			if (!L.uniform) {
 				aS = cf[0]; aW = cf[1]; aC = cf[2]; aE = cf[3]; aN = cf[4]; dinv = cf[5];
 				cf += MGB_COEF_STRIDE;
@@ -49,7 +49,7 @@ k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__
 			const double t0 = stencil5_ord(o0, aS, aW, aC, aE, aN, xm.x, xw, xc.x, xc.y, xn.x);
 			const double t1 = stencil5_ord(o1, aS, aW, aC, aE, aN, xm.y, xc.x, xc.y, xe, xn.y);
 			double2 out;
-			if (MODE == ST_APPLY) {
+			if (MODE == ST_APPLY || MODE == ST_APPLYDOT) {
 				out.x = t0; out.y = t1;
 			} else {
 				// r = b - A x   (KSPBuildResidual / Richardson: MatMult then VecAYPX(r, -1, b))
@@ -66,10 +66,11 @@ k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__
 			if (!in1) out.y = 0.0;
 			if (MODE == ST_RESNORM) acc += out.x * out.x + out.y * out.y;
 			else st2(y + (size_t)i * P + j0, out);
+			if (MODE == ST_APPLYDOT) acc += xc.x * out.x + xc.y * out.y;
 			xm = xc; xc = xn; xw = xnw; xe = xne; xp += P;
 		}
 	}
-	if (MODE == ST_RESNORM) {
+	if (MODE == ST_RESNORM || MODE == ST_APPLYDOT) {
 		const double s = block_sum<MGB_SB_THREADS>(acc);
 		if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 	}

@@ -482,3 +482,16 @@ def test_csr_on_strips_concatenates_to_the_reference_matrix(ranks, aggl):
     finally:
         e.close()
         o.close()
+
+
+@pytest.mark.parametrize("name", ["n129_l7_jacobi", "n101_l3_jacobi", "n1025_l10_jacobi", "n129_l7_cg_mg"])
+def test_without_bottom_kernel_matches_golden(name):
+    """-mgb_bottom 0: the smallest levels go through the fused legs (down to 1 x 1) instead of the cluster kernel."""
+    g = GOLD[name]
+    r = mgb.run_poisson(g["options"] + " -mgb_bottom 0")
+    assert r["num_iter"] == g["num_iter"]
+    want = _hex(g["rnorm_hex"])
+    ok = ~np.isnan(want)
+    assert np.allclose(r["rnorm"][ok], want[ok], rtol=RTOL, atol=RNORM_ATOL)
+    if "-cycle 0" in g["options"]:
+        assert hashlib.sha256(np.ascontiguousarray(r["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]

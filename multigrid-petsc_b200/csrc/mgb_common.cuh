@@ -27,7 +27,7 @@ struct LevelDev {
 	int pitch;           // doubles per row
 	int i0;              // global grid-row index of local row 0 (0 on a single GPU)
 	int gni;             // global number of grid rows of the level
-	int uniform;         // 1: every grid row has the same coefficients (mesh 0)
+	int uniform;         // 1: every grid row has the same coefficients (mesh 0); 2: ... and S = W = E = N = 2^m, C = -4 * 2^m
 	int rb;              // 1: red-black numbering (-map 3): row sums run in ascending RED-FIRST column order
 	const double *coef;  // MGB_COEF_STRIDE doubles per GLOBAL grid row
 };

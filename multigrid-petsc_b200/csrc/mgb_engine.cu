@@ -454,6 +454,13 @@ extern "C" int mgb_set_level_operator(mgb_engine *e, int level, const double *ro
 		c[7] = c[2];                // mdiag
 		if (memcmp(c, &g.coef_host[0], 5 * sizeof(double)) != 0) g.uniform = 0;
 	}
+	if (g.uniform) {
+		// power-of-two operator (every uniform 2^k - 1 grid): lets the fused kernel factor the coefficient out exactly
+		const double *c = &g.coef_host[0];
+		int ex = 0;
+		if (c[0] == c[1] && c[0] == c[3] && c[0] == c[4] && c[2] == -4.0 * c[0] && c[0] > 0.0 && frexp(c[0], &ex) == 0.5)
+			g.uniform = 2;
+	}
 	g.coef_set = true;
 	e->sor_omega = 1.0;
 	e->csr_built = false;

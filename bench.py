@@ -43,7 +43,7 @@ VCYCLE_BYTES_PER_FINE_UNKNOWN = 264    # unfused per-sweep byte co
 # (3 Jacobi sweeps + residual + restriction in one pass): it reads u and b once, writes u once and 1/4 coarse value
 FUSED_DOWN_BYTES_PER_UNKNOWN = 26      # 8 + 8 + 8 + 2
 FUSED_DOWN_UNFUSED_BYTES = 90          # the SURVEY.md 8d count of what it replaces: 3 x 24 (sweeps) + 18 (residual+restrict)
-NCU_TRAFFIC_FUSED_DOWN = 1.773e9       # dram read + write bytes per launch, ncu --set full (profiles/r1_ncu_fused_down.txt)
+NCU_TRAFFIC_FUSED_DOWN = 1.780e9       # dram read + write bytes per launch, ncu --set full (profiles/r1_ncu_fused_down.txt)
 
 
 def options(npts, levels, iters, extra=""):

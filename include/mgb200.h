@@ -173,7 +173,8 @@ typedef struct {
 } mgb_vcycle_params;
 
 /* rnorm: max_iter+1 doubles; on return rnorm[0..num_iter] are the RELATIVE residual norms
- * (src/solver.c:1554-1557).  seconds = wall time of the cycle loop only (src/solver.c:1526-1553). */
+ * (src/solver.c:1554-1557).  seconds = host wall time of the call; mgb_last_solve_ms() = device time of the cycle
+ * loop only, the region the reference brackets with MPI_Wtime (src/solver.c:1526-1553). */
 int  mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter, double *seconds);
 
 /* The same solve for a stream of independent right-hand sides, pipelined: the upload of right-hand side k+1 and the
@@ -210,7 +211,8 @@ double mgb_last_solve_ms(const mgb_engine *e);
  * 5 prolong+correct, 6 residual norm, 7 csr spmv (A), 8 nrm2, 9 dot, 10 axpy; fused legs (mgb_fused.cuh):
  * 11 down leg (3 sweeps + residual + restriction), 12 up leg (prolongation + 3 sweeps + residual norm),
  * 13 three sweeps, 14 one sweep, 15 down leg from a zero guess; 16 the persistent bottom kernel from `level`
- * down to the coarsest and back (mgb_coarse_cycle.cuh).  ms_per_launch is the average. */
+ * down to the coarsest and back (mgb_coarse_cycle.cuh); 17 ghost-row exchange of U alone, 18 nrm2 with the all-reduce
+ * over the ranks (row strips).  ms_per_launch is the average. */
 int  mgb_time_op(mgb_engine *e, int op, int level, int reps, double *ms_per_launch);
 
 #ifdef __cplusplus

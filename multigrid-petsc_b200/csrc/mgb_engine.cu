@@ -1596,7 +1596,7 @@ static std::vector<char> graph_key(mgb_engine *e, const mgb_vcycle_params *p)
 
 // the cycle loop of MultigridVcycle on the right-hand side in B[0] (ref: src/solver.c:1512-1558); rnorm holds
 // max_iter+1 entries and is returned normalised by rnorm[0]
-static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter)
+static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm, int *num_iter, bool mark_loop_start)
 {
 	Strip &s0 = e->strips[0];
 	// bnorm = ||b0|| ; u0 = 0 ; rnorm[0] = ||A0 u0 - b0||                                      (:1512-1520)
@@ -1610,6 +1610,8 @@ static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm
 	rnorm[0] = rn;
 	int iter = 0;
 	if (e->gcache.size() > 16) drop_graphs(e);
+	// the timed region of the reference starts here, after rnorm[0] (t0 = MPI_Wtime() at src/solver.c:1526)
+	if (mark_loop_start) CU(cudaEventRecord(s0.ev0, s0.stream));
 	while (iter < p->max_iter && 100000000.0 * bnorm > rn && rn > p->rtol * bnorm) {              // :1530
 		if (!p->use_graph || iter == 0) {
 			TRY(vcycle_body(e, p, iter == 0));
@@ -1666,8 +1668,7 @@ extern "C" int mgb_solve_vcycle(mgb_engine *e, const mgb_vcycle_params *p, doubl
 	Strip &s0 = e->strips[0];
 	TRY(sync(e));
 	const auto t0 = std::chrono::steady_clock::now();
-	CU(cudaEventRecord(s0.ev0, s0.stream));
-	TRY(vcycle_solve(e, p, rnorm, num_iter));
+	TRY(vcycle_solve(e, p, rnorm, num_iter, true));
 	CU(cudaEventRecord(s0.ev1, s0.stream));
 	CU(cudaStreamSynchronize(s0.stream));
 	const auto t1 = std::chrono::steady_clock::now();
@@ -1708,7 +1709,7 @@ extern "C" int mgb_solve_vcycle_many(mgb_engine *e, const mgb_vcycle_params *p, 
 		if (k + 1 < nrhs) TRY(upload(b_hosts[k + 1], SPARE_B, true));
 		int it = 0;
 		if (trace) fprintf(stderr, "[mgb] rhs %d: t=%.2f ms solve starts\n", k, now_ms());
-		TRY(vcycle_solve(e, p, rn.data(), &it));
+		TRY(vcycle_solve(e, p, rn.data(), &it, false));
 		if (trace) fprintf(stderr, "[mgb] rhs %d: t=%.2f ms solve done (%d cycles)\n", k, now_ms(), it);
 		if (num_iter) num_iter[k] = it;
 		if (final_rnorm) final_rnorm[k] = rn[it];

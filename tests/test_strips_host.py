@@ -104,3 +104,21 @@ def test_handle_exchange_world_size_2_gloo(tmp_path):
                           "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under multigrid-petsc_b200/ may import, link or execute it."""
+    pkg = os.path.join(ROOT, "multigrid-petsc_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        if os.sep + "lib" in d or "__pycache__" in d:
+            continue
+        for f in files:
+            if f.endswith((".py", ".c", ".h", ".cu", ".cuh")) or f == "Makefile":
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"\boracle\b|mgoracle|minipetsc|mg_oracle", txt):
+                    # mentions in comments that point at the oracle as the checker are fine; imports / includes / links are not
+                    for line in txt.splitlines():
+                        if re.search(r"^\s*(from|import)\s+oracle|#include\s*[\"<].*(mg_oracle|minipetsc|petscksp)|-lmgoracle|-[IL]\S*oracle|import_module\(.oracle", line):
+                            offenders.append((f, line.strip()))
+    assert not offenders, offenders

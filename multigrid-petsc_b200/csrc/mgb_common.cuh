@@ -38,6 +38,9 @@ __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<do
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+// fused multiply-add: used ONLY where the product is exact (one factor a power of two), so that the single rounding of
+// the sum gives the same bits as the reference's separate multiply and add
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 // (A x)_ij in MatMult_SeqAIJ order: ascending columns row-n, row-1, row, row+1, row+n
 // (ref call sites: src/solver.c:1516,1534,1545; the ghost zeros stand in for the entries fillJacobians drops)

@@ -130,6 +130,7 @@ struct mgb_engine {
 	bool peer_opened[MGB_MAX_RANKS] = {};
 	bool connected = false;
 	Stencil3 R3, P3; bool transfer_set = false;
+	bool transfer_pow2 = false;              // every res / pro weight is a power of two (exact products: the fused kernels may use fma)
 	double sor_omega = -1.0;
 	long long launches = 0;
 	double last_solve_ms = 0.0;
@@ -502,6 +503,11 @@ extern "C" int mgb_set_transfer(mgb_engine *e, const double res3[9], const doubl
 		if (res3[k] == 0.0 || pro3[k] == 0.0)
 			return fail(MGB_EINVAL, "zero transfer weight: the reference drops such entries from res/pro (src/solver.c:1086), not supported");
 		e->R3.w[k] = res3[k]; e->P3.w[k] = pro3[k];
+	}
+	e->transfer_pow2 = true;
+	for (int k = 0; k < 9; ++k) {
+		int ex = 0;
+		if (!(res3[k] > 0.0 && frexp(res3[k], &ex) == 0.5 && pro3[k] > 0.0 && frexp(pro3[k], &ex) == 0.5)) e->transfer_pow2 = false;
 	}
 	e->transfer_set = true;
 	e->csr_built = false;
@@ -1216,6 +1222,14 @@ static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 // ------------------------------------------------------------------------------------------------ fused legs (Jacobi)
 #define HALO_DEPTH MGB_GHOST_ROWS
 
+// the fused kernels' power-of-two path (OP = 2) also fuses the transfer weights into fma: only when those are exact too
+static LevelDev fused_ldev(const mgb_engine *e, const Strip &s, int l)
+{
+	LevelDev d = ldev(e, s, l);
+	if (d.uniform == 2 && e->L > 1 && !e->transfer_pow2) d.uniform = 1;
+	return d;
+}
+
 template <int D, int PRE, int POST>
 static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st)
 {
@@ -1259,7 +1273,7 @@ static int restrict_streamed(mgb_engine *e, int l, int bv, int xv)
 		SLevel &S = s.lev[l];
 		FusedArgs a; memset(&a, 0, sizeof a);
 		a.u_in = S.v[xv]; a.b = S.v[bv]; a.u_out = nullptr;
-		a.F = ldev(e, s, l); a.scale = 1.0; a.gni = g.gni;
+		a.F = fused_ldev(e, s, l); a.scale = 1.0; a.gni = g.gni;
 		a.rows = pick_rows(g, S.ni);
 		a.R3 = e->R3; a.P3 = e->P3;
 		size_t coff; a.C = coarse_view(e, s, l + 1, g.dist, &coff);
@@ -1295,7 +1309,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			SLevel &S = s.lev[l];
 			FusedArgs a; memset(&a, 0, sizeof a);
 			a.u_in = S.v[xv]; a.b = S.v[bv]; a.u_out = S.v[sv];
-			a.F = ldev(e, s, l); a.scale = sm->scale; a.gni = g.gni;
+			a.F = fused_ldev(e, s, l); a.scale = sm->scale; a.gni = g.gni;
 			a.rows = pick_rows(g, S.ni);
 			a.R3 = e->R3; a.P3 = e->P3;
 			int tiles = cdiv(g.pitch, FJ_VALID);

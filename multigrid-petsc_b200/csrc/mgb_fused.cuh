@@ -40,7 +40,7 @@
                                                   // neighbour reads are conflict-free 8-byte accesses)
 #define FJ_X(tid) ((tid) + 1)                     // left column (j0) of thread tid
 #define FJ_Y(tid) ((tid) + 1 + FJ_THREADS + 4)    // right column (j0+1) of thread tid
-template <int D> constexpr size_t jf_smem_bytes() { return sizeof(double) * ((size_t)2 * (D + 2) * FJ_PUB + (size_t)2 * FJ_NR * FJ_COLS); }
+template <int D> constexpr size_t jf_smem_bytes() { return sizeof(double) * ((size_t)2 * (D + 2) * FJ_PUB + (size_t)2 * FJ_NR * FJ_COLS + FJ_NR); }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS), bypassing L1: the input rows are consumed exactly once
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -50,6 +50,33 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TMA bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier.  One thread moves a whole 2 KB
+// input row: no per-thread LDGSTS, and the data is written to shared memory line by line instead of sector by sector
+// (ncu: the misaligned per-thread LDGSTS cost 14 shared-memory wavefronts per instruction instead of 4).
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"W_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@!p bra W_%=;\n"
+		"}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 
 enum { PRE_GIVEN = 0, PRE_ZERO = 1, PRE_PROLONG = 2, PRE_PROLONG_MULTADD = 3 };
 enum { POST_NONE = 0, POST_RESTRICT = 1, POST_NORM = 2 };
@@ -68,34 +95,51 @@ struct FusedArgs {
 	int gni;                 // global number of rows of the fine level
 };
 
-struct Coef { double aS, aW, aC, aE, aN, dinv; };
+struct Coef { double aS, aW, aC, aE, aN, dinv, nS; };   // nS = -aS (power-of-two path)
 __device__ __forceinline__ Coef load_coef(const LevelDev &L, int gni, int grow)
 {
 	const int g = grow < 0 ? 0 : (grow >= gni ? gni - 1 : grow);
 	const double *cf = L.coef + (size_t)g * MGB_COEF_STRIDE;
-	Coef c; c.aS = cf[0]; c.aW = cf[1]; c.aC = cf[2]; c.aE = cf[3]; c.aN = cf[4]; c.dinv = cf[5];
+	Coef c; c.aS = cf[0]; c.aW = cf[1]; c.aC = cf[2]; c.aE = cf[3]; c.aN = cf[4]; c.dinv = cf[5]; c.nS = -cf[0];
 	return c;
 }
 
 // u + pro * uc at fine columns j0, j0+1 -- the arithmetic of k_prolong_add, natural numbering.
 // odd fine row: cm / c0 = coarse row (i-1)/2, columns J0-1 / J0.  even fine row: (am, a0) = coarse row i/2-1, (bm, b0) = row i/2.
-template <int MULTADD>
+// TP2: every weight is a power of two (the reference's stencils: 1/4, 1/2, 1): the products are exact, so
+// add(x, mul(w, c)) == fma(w, c, x) bit for bit, and mul(1.0, x) == x.
+template <int MULTADD, bool TP2>
 __device__ __forceinline__ double2 prolonged_odd(double2 u, double cmv, double c0v, const Stencil3 &Pw)
 {
+	double e0, e1;
+	if (TP2) {
+		if (MULTADD) { e0 = fma_rn(Pw.w[3 + 0], c0v, fma_rn(Pw.w[3 + 2], cmv, u.x)); e1 = fma_rn(Pw.w[3 + 1], c0v, u.y); }
+		else { e0 = add(u.x, fma_rn(Pw.w[3 + 0], c0v, mul(Pw.w[3 + 2], cmv))); e1 = fma_rn(Pw.w[3 + 1], c0v, u.y); }
+		return make_double2(e0, e1);
+	}
 	const double cm = mul(Pw.w[3 + 2], cmv), c0 = mul(Pw.w[3 + 0], c0v);
 	const double s0 = mul(Pw.w[3 + 1], c0v);
-	double e0, e1;
 	if (MULTADD) { e0 = add(add(u.x, cm), c0); e1 = add(u.y, s0); }
 	else { e0 = add(u.x, mul(1.0, add(cm, c0))); e1 = add(u.y, mul(1.0, s0)); }
 	return make_double2(e0, e1);
 }
-template <int MULTADD>
+template <int MULTADD, bool TP2>
 __device__ __forceinline__ double2 prolonged_even(double2 u, double amv, double a0v, double bmv, double b0v, const Stencil3 &Pw)
 {
+	double e0, e1;
+	if (TP2) {
+		if (MULTADD) {
+			e0 = fma_rn(Pw.w[0 + 0], b0v, fma_rn(Pw.w[0 + 2], bmv, fma_rn(Pw.w[6 + 0], a0v, fma_rn(Pw.w[6 + 2], amv, u.x))));
+			e1 = fma_rn(Pw.w[0 + 1], b0v, fma_rn(Pw.w[6 + 1], a0v, u.y));
+		} else {
+			e0 = add(u.x, fma_rn(Pw.w[0 + 0], b0v, fma_rn(Pw.w[0 + 2], bmv, fma_rn(Pw.w[6 + 0], a0v, mul(Pw.w[6 + 2], amv)))));
+			e1 = add(u.y, fma_rn(Pw.w[0 + 1], b0v, mul(Pw.w[6 + 1], a0v)));
+		}
+		return make_double2(e0, e1);
+	}
 	const double am = mul(Pw.w[6 + 2], amv), a0 = mul(Pw.w[6 + 0], a0v);
 	const double bm = mul(Pw.w[0 + 2], bmv), b0 = mul(Pw.w[0 + 0], b0v);
 	const double sa = mul(Pw.w[6 + 1], a0v), sb = mul(Pw.w[0 + 1], b0v);
-	double e0, e1;
 	if (MULTADD) { e0 = add(add(add(add(u.x, am), a0), bm), b0); e1 = add(add(u.y, sa), sb); }
 	else { e0 = add(u.x, mul(1.0, add(add(add(am, a0), bm), b0))); e1 = add(u.y, mul(1.0, add(sa, sb))); }
 	return make_double2(e0, e1);
@@ -117,6 +161,9 @@ struct JfBlock {
 	int tid, c0, j0, y0, y1;
 	ptrdiff_t P;
 	bool in0, in1, ld_ok, st_ok;
+	bool tma;                // input rows arrive by TMA bulk copies (pitch >= FJ_COLS) instead of per-thread cp.async
+	int rbase;               // first row of the input rings: row i lives in slot (i - rbase) & (FJ_NR - 1)
+	unsigned long long *bar; // FJ_NR mbarriers, one per ring slot (TMA path)
 	Coef cu;                 // coefficients of a uniform operator, held in ordinary (per-thread) registers
 	double scale;
 	double sd;               // scale * dinv (power-of-two operator: exact, see jf_point)
@@ -132,8 +179,9 @@ template <int OP>
 __device__ __forceinline__ double jf_residual(const Coef &cf, double b, double xS, double xW, double xC, double xE, double xN)
 {
 	if (OP == 2) {
-		const double t = add(add(add(add(xS, xW), mul(-4.0, xC)), xE), xN);
-		return sub(b, mul(cf.aS, t));
+		// -4 xC and c t are exact products: add(s, mul(-4, xC)) == fma(-4, xC, s) and sub(b, mul(c, t)) == fma(-c, t, b), same bits
+		const double t = add(add(fma_rn(-4.0, xC, add(xS, xW)), xE), xN);
+		return fma_rn(cf.nS, t, b);
 	}
 	return sub(b, stencil5(cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xS, xW, xC, xE, xN));
 }
@@ -155,9 +203,24 @@ template <int PRE, bool MASK>
 __device__ __forceinline__ void jf_request(const FusedArgs &A, const JfBlock &B, double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int i)
 {
 	const LevelDev &F = A.F;
-	const int slot = i & (FJ_NR - 1);
+	const int slot = (i - B.rbase) & (FJ_NR - 1);
+	if (!MASK || B.tma) {
+		// one thread, one 2 KB bulk copy per array.  Rows outside the arrays are clamped (their values are masked to zero at
+		// stage 0 / at every stage of an out-of-grid row); columns outside the grid read the neighbouring rows' memory, which
+		// lies inside the allocation whenever pitch >= FJ_COLS, and are masked the same way.
+		if (B.tid == 0) {
+			int ic = i;
+			if (MASK) ic = ic < -MGB_GHOST_ROWS ? -MGB_GHOST_ROWS : (ic > F.ni + MGB_GHOST_ROWS - 1 ? F.ni + MGB_GHOST_ROWS - 1 : ic);
+			const ptrdiff_t o = (ptrdiff_t)ic * B.P + (B.c0 - FJ_HALO);
+			unsigned long long *bar = B.bar + slot;
+			mbar_expect_tx(bar, (PRE != PRE_ZERO ? 2u : 1u) * (unsigned)(FJ_COLS * sizeof(double)));
+			if (PRE != PRE_ZERO) bulk_g2s(&in_u[slot][0], A.u_in + o, FJ_COLS * sizeof(double), bar);
+			bulk_g2s(&in_b[slot][0], A.b + o, FJ_COLS * sizeof(double), bar);
+		}
+		return;
+	}
 	bool ok = true;
-	if (MASK) {
+	{
 		const int g = F.i0 + i;
 		ok = B.ld_ok && g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
 	}
@@ -169,6 +232,15 @@ __device__ __forceinline__ void jf_request(const FusedArgs &A, const JfBlock &B,
 		*reinterpret_cast<double2 *>(&in_b[slot][2 * B.tid]) = make_double2(0.0, 0.0);
 	}
 	cp_async_commit();
+}
+// row i of the input rings has arrived (TMA: phase parity of its slot's mbarrier; cp.async: at most FJ_PF younger groups pending)
+template <bool MASK>
+__device__ __forceinline__ void jf_arrived(const JfBlock &B, int i)
+{
+	if (!MASK || B.tma) {
+		const int k = i - B.rbase;
+		mbar_wait(B.bar + (k & (FJ_NR - 1)), (unsigned)(k >> 3) & 1u);
+	} else cp_async_wait<FJ_PF>();
 }
 
 template <int D, int PRE, int POST, bool MASK, int OP, int K>
@@ -187,17 +259,17 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	};
 	// ---- rows t+FJ_PF are requested; stage 0 of row t and b of row t-1 have arrived in the input rings
 	jf_request<PRE, MASK>(A, B, in_u, in_b, t + FJ_PF);
-	cp_async_wait<FJ_PF>();
+	jf_arrived<MASK>(B, t);
 	double2 u0 = make_double2(0.0, 0.0);
-	if (PRE != PRE_ZERO) u0 = *reinterpret_cast<const double2 *>(&in_u[t & (FJ_NR - 1)][2 * tid]);
+	if (PRE != PRE_ZERO) u0 = *reinterpret_cast<const double2 *>(&in_u[(t - B.rbase) & (FJ_NR - 1)][2 * tid]);
 	const double2 bold = S.bq[(K + 3) & 3];               // b of row t-5, evicted now (the residual of a D = 3 leg still needs it)
-	S.bq[(K + 3) & 3] = *reinterpret_cast<const double2 *>(&in_b[(t - 1) & (FJ_NR - 1)][2 * tid]);   // slot of row t-1
+	S.bq[(K + 3) & 3] = *reinterpret_cast<const double2 *>(&in_b[(t - 1 - B.rbase) & (FJ_NR - 1)][2 * tid]);   // slot of row t-1
 	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
 		// t = 4m + K: coarse rows T-1, T, T+1 with T = 2m are in cq[0..2] (fine rows t..t+3 of the group need exactly these)
-		if (K == 0) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[0].x, S.cq[0].y, S.cq[1].x, S.cq[1].y, A.P3);
-		if (K == 1) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[1].x, S.cq[1].y, A.P3);
-		if (K == 2) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[1].x, S.cq[1].y, S.cq[2].x, S.cq[2].y, A.P3);
-		if (K == 3) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[2].x, S.cq[2].y, A.P3);
+		if (K == 0) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[0].x, S.cq[0].y, S.cq[1].x, S.cq[1].y, A.P3);
+		if (K == 1) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[1].x, S.cq[1].y, A.P3);
+		if (K == 2) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[1].x, S.cq[1].y, S.cq[2].x, S.cq[2].y, A.P3);
+		if (K == 3) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[2].x, S.cq[2].y, A.P3);
 	}
 	if (MASK) {
 		const bool rk = row_ok(t);
@@ -259,7 +331,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 			if (!B.in1 || !rok) res.y = 0.0;
 		}
 		if (POST == POST_NORM) {
-			if (B.st_ok && rho >= B.y0 && rho < B.y1) S.acc += res.x * res.x + res.y * res.y;
+			if (B.st_ok && rho >= B.y0 && rho < B.y1) S.acc = fma_rn(res.y, res.y, fma_rn(res.x, res.x, S.acc));   // the norm is compared to 1e-10, not bitwise
 		}
 		// neighbours of stage D, row t-D-1 (published in the previous step): the centre row of the next step's residual
 		S.wer[0] = shp[D][FJ_Y(tid - 1)];
@@ -276,14 +348,26 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 			if (B.st_ok && I >= (B.y0 >> 1) && I < (B.y1 >> 1) && I < A.C.ni && J < A.C.pitch) {
 				constexpr int R0 = (RP + 2) & 3, R1 = (RP + 3) & 3;    // rows rp-2, rp-1
 				double sum = mul(A.R3.w[0], S.rw[R0][0]);
-				sum = add(sum, mul(A.R3.w[1], S.rw[R0][1]));
-				sum = add(sum, mul(A.R3.w[2], S.rw[R0][2]));
-				sum = add(sum, mul(A.R3.w[3], S.rw[R1][0]));
-				sum = add(sum, mul(A.R3.w[4], S.rw[R1][1]));
-				sum = add(sum, mul(A.R3.w[5], S.rw[R1][2]));
-				sum = add(sum, mul(A.R3.w[6], S.rw[RP][0]));
-				sum = add(sum, mul(A.R3.w[7], S.rw[RP][1]));
-				sum = add(sum, mul(A.R3.w[8], S.rw[RP][2]));
+				if (OP == 2) {
+					// power-of-two weights (1/16, 1/8, 1/4): exact products, add(sum, mul(w, r)) == fma(w, r, sum)
+					sum = fma_rn(A.R3.w[1], S.rw[R0][1], sum);
+					sum = fma_rn(A.R3.w[2], S.rw[R0][2], sum);
+					sum = fma_rn(A.R3.w[3], S.rw[R1][0], sum);
+					sum = fma_rn(A.R3.w[4], S.rw[R1][1], sum);
+					sum = fma_rn(A.R3.w[5], S.rw[R1][2], sum);
+					sum = fma_rn(A.R3.w[6], S.rw[RP][0], sum);
+					sum = fma_rn(A.R3.w[7], S.rw[RP][1], sum);
+					sum = fma_rn(A.R3.w[8], S.rw[RP][2], sum);
+				} else {
+					sum = add(sum, mul(A.R3.w[1], S.rw[R0][1]));
+					sum = add(sum, mul(A.R3.w[2], S.rw[R0][2]));
+					sum = add(sum, mul(A.R3.w[3], S.rw[R1][0]));
+					sum = add(sum, mul(A.R3.w[4], S.rw[R1][1]));
+					sum = add(sum, mul(A.R3.w[5], S.rw[R1][2]));
+					sum = add(sum, mul(A.R3.w[6], S.rw[RP][0]));
+					sum = add(sum, mul(A.R3.w[7], S.rw[RP][1]));
+					sum = add(sum, mul(A.R3.w[8], S.rw[RP][2]));
+				}
 				A.bc[(size_t)I * A.C.pitch + J] = (J < A.C.nj) ? sum : 0.0;
 			}
 		}
@@ -316,6 +400,7 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 	};
 	// rows t0-1 .. t0+FJ_PF-1 are requested up front, one commit group each (row t0-1 only feeds the b ring)
 	for (int i = t0 - 1; i < t0 + FJ_PF; ++i) jf_request<PRE, MASK>(A, B, in_u, in_b, i);
+	if (!MASK || B.tma) jf_arrived<MASK>(B, t0 - 1);     // b of row t0-1 is read at step t0 (each step waits for its own row only)
 	// coarse values of one coarse row (columns J0-1, J0); rows outside the coarse arrays are clamped (their fine rows are masked)
 	auto load_c = [&](int I) -> double2 {
 		if (MASK) {
@@ -340,6 +425,11 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 		jf_step<D, PRE, POST, MASK, OP, 3>(A, B, S, sh, in_u, in_b, t + 3);
 		if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) { S.cq[0] = S.cq[2]; S.cq[1] = S.cn[0]; S.cq[2] = S.cn[1]; }
 	}
+	if (!MASK || B.tma) {
+		// the FJ_PF rows requested beyond the last step: a block must not retire with bulk copies into its shared memory in flight
+		const int tl = t0 + ((t1 - t0) & ~3) + 3;
+		for (int i = tl + 1; i <= tl + FJ_PF; ++i) jf_arrived<MASK>(B, i);
+	}
 	if (POST == POST_NORM) {
 		const double s = block_sum<FJ_THREADS>(S.acc);
 		if (B.tid == 0) A.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
@@ -347,7 +437,7 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 }
 
 template <int D, int PRE, int POST>
-__global__ void __launch_bounds__(FJ_THREADS)
+__global__ void __launch_bounds__(FJ_THREADS, 4)
 k_jfused(FusedArgs A)
 {
 	// dynamic shared memory: rows produced in the previous step, per stage (0..D) and the residual row (index D+1),
@@ -358,6 +448,13 @@ k_jfused(FusedArgs A)
 	double (*in_b)[FJ_COLS] = in_u + FJ_NR;
 	const LevelDev &F = A.F;
 	JfBlock B;
+	B.bar = reinterpret_cast<unsigned long long *>(in_b + FJ_NR);
+	B.tma = F.pitch >= FJ_COLS;
+	if (threadIdx.x == 0) {
+		for (int k = 0; k < FJ_NR; ++k) mbar_init(B.bar + k, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
 	B.tid = threadIdx.x;
 	B.c0 = blockIdx.x * FJ_VALID;                         // first valid column of the tile
 	B.j0 = B.c0 - FJ_HALO + 2 * B.tid;                    // this thread's columns j0, j0+1 (j0 even)
@@ -370,11 +467,12 @@ k_jfused(FusedArgs A)
 	{
 		const Coef c = load_coef(F, A.gni, F.i0);         // uniform operator: one coefficient set
 		B.cu.aS = vreg(c.aS); B.cu.aW = vreg(c.aW); B.cu.aC = vreg(c.aC); B.cu.aE = vreg(c.aE); B.cu.aN = vreg(c.aN);
-		B.cu.dinv = vreg(c.dinv); B.scale = vreg(A.scale); B.sd = vreg(A.scale * c.dinv);
+		B.cu.dinv = vreg(c.dinv); B.cu.nS = vreg(c.nS); B.scale = vreg(A.scale); B.sd = vreg(A.scale * c.dinv);
 	}
 	// steps: stage 0 of row y0-D-1 is the first needed, the restriction of row y1 completes at step y1+D+3;
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
 	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 3;
+	B.rbase = tb - 1;
 	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
 	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
 	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 4 + FJ_PF < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) &&

@@ -58,11 +58,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
 	asm volatile(
 		"{\n"
@@ -70,12 +70,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 		"W_%=:\n"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
 		"@!p bra W_%=;\n"
-		"}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+		"}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar)
+__device__ __forceinline__ void bulk_g2s(unsigned smem, const void *gmem, unsigned bytes, unsigned bar)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+	             ::"r"(smem), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
 enum { PRE_GIVEN = 0, PRE_ZERO = 1, PRE_PROLONG = 2, PRE_PROLONG_MULTADD = 3 };
@@ -164,6 +164,8 @@ struct JfBlock {
 	bool tma;                // input rows arrive by TMA bulk copies (pitch >= FJ_COLS) instead of per-thread cp.async
 	int rbase;               // first row of the input rings: row i lives in slot (i - rbase) & (FJ_NR - 1)
 	unsigned long long *bar; // FJ_NR mbarriers, one per ring slot (TMA path)
+	unsigned s_bar, s_u, s_b; // 32-bit shared-window addresses of the mbarriers and of the two input rings
+	const double *g_u, *g_b; // column c0 - FJ_HALO of row 0 of u_in / b
 	Coef cu;                 // coefficients of a uniform operator, held in ordinary (per-thread) registers
 	double scale;
 	double sd;               // scale * dinv (power-of-two operator: exact, see jf_point)
@@ -199,7 +201,7 @@ __device__ __forceinline__ double vreg(double x) { double y; asm volatile("mov.f
 
 // one row step; K = t & 3 (compile time), MASK = the block touches the outside of the grid
 // request rows `i` of u and b into the input rings (one commit group per call, possibly empty)
-template <int PRE, bool MASK>
+template <int PRE, bool MASK, int KW>
 __device__ __forceinline__ void jf_request(const FusedArgs &A, const JfBlock &B, double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int i)
 {
 	const LevelDev &F = A.F;
@@ -207,15 +209,17 @@ __device__ __forceinline__ void jf_request(const FusedArgs &A, const JfBlock &B,
 	if (!MASK || B.tma) {
 		// one thread, one 2 KB bulk copy per array.  Rows outside the arrays are clamped (their values are masked to zero at
 		// stage 0 / at every stage of an out-of-grid row); columns outside the grid read the neighbouring rows' memory, which
-		// lies inside the allocation whenever pitch >= FJ_COLS, and are masked the same way.
-		if (B.tid == 0) {
+		// lies inside the allocation whenever pitch >= FJ_COLS, and are masked the same way.  The issuing warp rotates with
+		// the step (KW = t & 3): the four warps of a block sit on the four schedulers of the SM, so no scheduler carries
+		// the request instructions of every resident block.
+		if (B.tid == KW * 32) {
 			int ic = i;
 			if (MASK) ic = ic < -MGB_GHOST_ROWS ? -MGB_GHOST_ROWS : (ic > F.ni + MGB_GHOST_ROWS - 1 ? F.ni + MGB_GHOST_ROWS - 1 : ic);
-			const ptrdiff_t o = (ptrdiff_t)ic * B.P + (B.c0 - FJ_HALO);
-			unsigned long long *bar = B.bar + slot;
+			const ptrdiff_t o = (ptrdiff_t)ic * B.P;
+			const unsigned bar = B.s_bar + slot * 8u, so = (unsigned)slot * (unsigned)(FJ_COLS * sizeof(double));
 			mbar_expect_tx(bar, (PRE != PRE_ZERO ? 2u : 1u) * (unsigned)(FJ_COLS * sizeof(double)));
-			if (PRE != PRE_ZERO) bulk_g2s(&in_u[slot][0], A.u_in + o, FJ_COLS * sizeof(double), bar);
-			bulk_g2s(&in_b[slot][0], A.b + o, FJ_COLS * sizeof(double), bar);
+			if (PRE != PRE_ZERO) bulk_g2s(B.s_u + so, B.g_u + o, FJ_COLS * sizeof(double), bar);
+			bulk_g2s(B.s_b + so, B.g_b + o, FJ_COLS * sizeof(double), bar);
 		}
 		return;
 	}
@@ -239,7 +243,7 @@ __device__ __forceinline__ void jf_arrived(const JfBlock &B, int i)
 {
 	if (!MASK || B.tma) {
 		const int k = i - B.rbase;
-		mbar_wait(B.bar + (k & (FJ_NR - 1)), (unsigned)(k >> 3) & 1u);
+		mbar_wait(B.s_bar + 8u * (unsigned)(k & (FJ_NR - 1)), (unsigned)(k >> 3) & 1u);
 	} else cp_async_wait<FJ_PF>();
 }
 
@@ -258,7 +262,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 		return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
 	};
 	// ---- rows t+FJ_PF are requested; stage 0 of row t and b of row t-1 have arrived in the input rings
-	jf_request<PRE, MASK>(A, B, in_u, in_b, t + FJ_PF);
+	jf_request<PRE, MASK, K>(A, B, in_u, in_b, t + FJ_PF);
 	jf_arrived<MASK>(B, t);
 	double2 u0 = make_double2(0.0, 0.0);
 	if (PRE != PRE_ZERO) u0 = *reinterpret_cast<const double2 *>(&in_u[(t - B.rbase) & (FJ_NR - 1)][2 * tid]);
@@ -399,7 +403,7 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 		return g >= 0 && g < A.gni && i >= -MGB_GHOST_ROWS && i < F.ni + MGB_GHOST_ROWS;
 	};
 	// rows t0-1 .. t0+FJ_PF-1 are requested up front, one commit group each (row t0-1 only feeds the b ring)
-	for (int i = t0 - 1; i < t0 + FJ_PF; ++i) jf_request<PRE, MASK>(A, B, in_u, in_b, i);
+	for (int i = t0 - 1; i < t0 + FJ_PF; ++i) jf_request<PRE, MASK, 0>(A, B, in_u, in_b, i);
 	if (!MASK || B.tma) jf_arrived<MASK>(B, t0 - 1);     // b of row t0-1 is read at step t0 (each step waits for its own row only)
 	// coarse values of one coarse row (columns J0-1, J0); rows outside the coarse arrays are clamped (their fine rows are masked)
 	auto load_c = [&](int I) -> double2 {
@@ -449,6 +453,8 @@ k_jfused(FusedArgs A)
 	const LevelDev &F = A.F;
 	JfBlock B;
 	B.bar = reinterpret_cast<unsigned long long *>(in_b + FJ_NR);
+	B.s_bar = (unsigned)__cvta_generic_to_shared(B.bar);
+	B.s_u = (unsigned)__cvta_generic_to_shared(in_u); B.s_b = (unsigned)__cvta_generic_to_shared(in_b);
 	B.tma = F.pitch >= FJ_COLS;
 	if (threadIdx.x == 0) {
 		for (int k = 0; k < FJ_NR; ++k) mbar_init(B.bar + k, 1);
@@ -473,6 +479,7 @@ k_jfused(FusedArgs A)
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
 	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 3;
 	B.rbase = tb - 1;
+	B.g_u = A.u_in + (B.c0 - FJ_HALO); B.g_b = A.b + (B.c0 - FJ_HALO);
 	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
 	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
 	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 4 + FJ_PF < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) &&

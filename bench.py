@@ -43,7 +43,24 @@ VCYCLE_BYTES_PER_FINE_UNKNOWN = 264    # unfused per-sweep byte co
 # (3 Jacobi sweeps + residual + restriction in one pass): it reads u and b once, writes u once and 1/4 coarse value
 FUSED_DOWN_BYTES_PER_UNKNOWN = 26      # 8 + 8 + 8 + 2
 FUSED_DOWN_UNFUSED_BYTES = 90          # the SURVEY.md 8d count of what it replaces: 3 x 24 (sweeps) + 18 (residual+restrict)
-NCU_TRAFFIC_FUSED_DOWN = 1.780e9       # dram read + write bytes per launch, ncu --set full (profiles/r1_ncu_fused_down.txt)
+NCU_FUSED_DOWN_SUMMARY = os.path.join(ROOT, "profiles", "r2_ncu_fused_down.txt")   # ncu --set full summary of that kernel
+WORKLOAD = f"2D Poisson {NPTS}^2 fp64, {LEVELS}-level V(3,3), Richardson+Jacobi 0.8 (BASELINE configs[3])"
+METRIC = "V-cycles/sec (fp64, 8193^2 grid)"
+PARITY_TOL = 1e-10                     # north_star: per-cycle residual norms within 1e-10 relative
+MGJ = ("-mg_levels_ksp_type richardson -mg_levels_pc_type jacobi -mg_levels_ksp_richardson_scale 0.8 "
+       "-mg_levels_ksp_max_it 3")
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu summary"""
+    try:
+        for line in open(NCU_FUSED_DOWN_SUMMARY):
+            m = re.match(r"\s*traffic = dram read \+ write\s+([0-9.eE+]+)\s+byte", line)
+            if m:
+                return float(m.group(1)), os.path.relpath(NCU_FUSED_DOWN_SUMMARY, ROOT)
+    except OSError:
+        pass
+    return None, None
 
 
 def options(npts, levels, iters, extra=""):
@@ -110,8 +127,35 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference
-def run_reference(npts, levels, cycles, threads=None):
-    """The reference's own driver on the host cores: returns (V-cycles/s, cores, kind, walltime, cycles)."""
+def _record_paths(tag):
+    return [os.path.join(ROOT, "gpurun_out", f"ref_record_{tag}.json"), os.path.join(tempfile.gettempdir(), f"mgb200_ref_record_{tag}.json")]
+
+
+def save_record(tag, rec):
+    for path in _record_paths(tag):
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            json.dump(rec, open(path, "w"))
+        except OSError:
+            pass
+
+
+def load_record(tag, max_age_s=6 * 3600):
+    """what a reference run on THIS box left behind (bench.py --impl reference runs right before the B200 arm)"""
+    for path in _record_paths(tag):
+        try:
+            if time.time() - os.path.getmtime(path) <= max_age_s:
+                rec = json.load(open(path))
+                if rec.get("host") == os.uname().nodename:
+                    return rec
+        except (OSError, ValueError):
+            pass
+    return None
+
+
+def run_reference_opts(opts, threads=None):
+    """The reference's own driver (oracle/_ref/poisson_ref: unmodified src/*.c over the in-repo mini-PETSc) with the
+    given poisson.in options on the host cores.  Returns dict(iters, wall, rnorm[], error[3], cores, kind)."""
     from oracle import ref_binary_path
     ncores = threads or os.cpu_count() or 1
     env = dict(os.environ, OMP_NUM_THREADS=str(ncores))
@@ -119,42 +163,239 @@ def run_reference(npts, levels, cycles, threads=None):
     if os.path.exists(exe):
         with tempfile.TemporaryDirectory() as d:
             with open(os.path.join(d, "poisson.in"), "w") as f:
-                f.write(options_file(options(npts, levels, cycles)))
+                f.write(options_file(opts))
+            # the solution / grid dumps (~27 bytes per unknown each, src/solver.c:1337-1346) are not needed here: they go to /dev/null
+            for name in ("uData.dat", "XgridData.dat", "YgridData.dat"):
+                os.symlink(os.devnull, os.path.join(d, name))
             out = subprocess.run([exe], cwd=d, env=env, capture_output=True, text=True, timeout=3000)
-        m = re.search(r"Solver walltime:\s+([0-9.eE+-]+)", out.stdout)
-        it = re.search(r"Number of iterations:\s+(\d+)", out.stdout)
-        if out.returncode != 0 or not m or not it:
-            raise RuntimeError("reference run failed: " + out.stderr[-400:] + out.stdout[-400:])
-        wall, done = float(m.group(1)), int(it.group(1))
-        return done / wall, ncores, "reference", wall, done
+            m = re.search(r"Solver walltime:\s+([0-9.eE+-]+)", out.stdout)
+            it = re.search(r"Number of iterations:\s+(\d+)", out.stdout)
+            if out.returncode != 0 or not m or not it:
+                raise RuntimeError("reference run failed: " + out.stderr[-400:] + out.stdout[-400:])
+            rn = [float(t) for t in open(os.path.join(d, "rData.dat")).read().split()]
+            er = [float(t) for t in open(os.path.join(d, "eData.dat")).read().split()]
+        return {"iters": int(it.group(1)), "wall": float(m.group(1)), "rnorm": rn, "error": er, "cores": ncores, "kind": "reference"}
     # no oracle/_ref on this machine: the oracle's restatement of the same loop (kind "port")
     from oracle import Oracle
-    o = Oracle(options(npts, levels, cycles))
+    o = Oracle(opts)
     t0 = time.perf_counter()
-    done, _ = o.solve()
+    done, rn = o.solve()
     wall = time.perf_counter() - t0
+    _, err = o.postprocess()
     o.close()
-    return done / wall, ncores, "port", wall, done
+    return {"iters": int(done), "wall": wall, "rnorm": [float(x) for x in rn], "error": [float(x) for x in err], "cores": ncores, "kind": "port"}
+
+
+def run_reference(npts, levels, cycles, threads=None):
+    """cycle-0 workload of this bench on the host cores: returns (V-cycles/s, cores, kind, walltime, cycles)."""
+    r = run_reference_opts(options(npts, levels, cycles), threads)
+    run_reference.last = r
+    return r["iters"] / r["wall"], r["cores"], r["kind"], r["wall"], r["iters"]
 
 
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if a.workload == "cg":
+        return reference_arm_cg(a)
     cycles = max(1, min(a.steps, 3))
     n = NPTS - 2
     v, cores, kind, wall, done = run_reference(NPTS, LEVELS, cycles)
+    r = run_reference.last
     sample = (f"{done} V-cycles of the full {NPTS}^2 / {LEVELS}-level workload, cycle loop only as the reference times it "
               f"(src/solver.c:1526-1553); {kind}: reference src/*.c over the in-repo mini-PETSc (real PETSc absent), "
               f"OpenMP over {cores} host threads")
-    line = {"impl": "reference", "metric": "V-cycles/sec (fp64, 8193^2 grid)", "value": v, "unit": "V-cycles/s",
+    save_record(f"vcycle_{NPTS}", {"host": os.uname().nodename, "npts": NPTS, "levels": LEVELS, "cycles": done, "rnorm": r["rnorm"],
+                                   "value": v, "cores": cores, "kind": kind, "wall": wall, "sample": sample})
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "V-cycles/s",
             "n_gpus": a.gpus, "steps": done, "warmup": 0, "ms_per_step": 1e3 * wall / done, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"2D Poisson {NPTS}^2 fp64, {LEVELS}-level V(3,3), Richardson+Jacobi 0.8", "unknowns": n * n},
+            "config": {"workload": WORKLOAD, "unknowns": n * n},
             "cpu_baseline": {"value": v, "unit": "V-cycles/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "rnorm": r["rnorm"][: done + 1], "gpu_launches": 0}
     print(json.dumps(line))
+    return 0
+
+
+def parity_block(rn_gpu, rec):
+    """per-cycle relative residual norms of the B200 arm against the reference run's rData.dat on the same input"""
+    k = min(len(rn_gpu), len(rec["rnorm"]), rec["cycles"] + 1)
+    diffs = [abs(float(rn_gpu[i]) - rec["rnorm"][i]) / abs(rec["rnorm"][i]) for i in range(k)]
+    return {"against": f"oracle/_ref/poisson_ref ({rec['kind']}: reference src/*.c over mini-PETSc) on this box, same {rec['npts']}^2 input",
+            "cycles": k - 1, "max_rel_diff": max(diffs), "tol": PARITY_TOL, "ok": bool(max(diffs) <= PARITY_TOL),
+            "rnorm_b200": [float(x) for x in rn_gpu[:k]], "rnorm_reference": rec["rnorm"][:k]}
+
+
+def cpu_block(a):
+    """cpu_baseline + the record the parity check runs against: what `--impl reference` left on this box, else run it now"""
+    rec = load_record(f"vcycle_{NPTS}")
+    how = "measured by the preceding `bench.py --impl reference` run on this box"
+    if rec is None:
+        if a.no_cpu_baseline or a.profile:
+            return None, None
+        v, cores, kind, wall, done = run_reference(NPTS, LEVELS, 3)
+        r = run_reference.last
+        rec = {"host": os.uname().nodename, "npts": NPTS, "levels": LEVELS, "cycles": done, "rnorm": r["rnorm"], "value": v,
+               "cores": cores, "kind": kind, "wall": wall,
+               "sample": (f"{done} V-cycles of the full {NPTS}^2 / {LEVELS}-level workload, cycle loop only (src/solver.c:1526-1553); "
+                          f"{kind}: reference src/*.c over the in-repo mini-PETSc (real PETSc absent), OpenMP over {cores} host threads")}
+        save_record(f"vcycle_{NPTS}", rec)
+        how = "measured inside this run"
+    cpu = {"value": rec["value"], "unit": "V-cycles/s", "cores": rec["cores"], "kind": rec["kind"],
+           "sample": rec["sample"] + "; " + how + " (mini-PETSc, not real PETSc: a stated baseline)"}
+    return cpu, rec
+
+
+def bits_fingerprint(u):
+    """partition-independent, bit-sensitive checksum of an fp64 array: (sum, xor) of the 64-bit patterns"""
+    import numpy as np
+    w = np.ascontiguousarray(u, dtype="<f8").view(np.uint64).reshape(-1)
+    return int(np.add.reduce(w, dtype=np.uint64)), int(np.bitwise_xor.reduce(w))
+
+
+
+# ---------------------------------------------------------------------------------------------- CG workload
+MGC1 = "-mg_coarse_ksp_type richardson -mg_coarse_pc_type jacobi -mg_coarse_ksp_max_it 1"   # exact on the 1x1 coarsest grid
+
+
+def cg_levels(npts):
+    return (npts - 1).bit_length() - 1          # down to the 1 x 1 grid: 12 levels at 4097, 13 at 8193
+
+
+def cg_options(npts, iters=100, extra=""):
+    L = cg_levels(npts)
+    return (f"-npts {npts} -mesh 0 -iter {iters} -grids {L} -levels {L} -cycle 8 -map 2 -v 3,3 -moreNorm 0 "
+            f"-ksp_type cg -ksp_rtol 1e-10 {MGJ} {MGC1} {extra}").strip()
+
+
+def cg_workload(npts):
+    return (f"2D Poisson {npts}^2 fp64, CG preconditioned by one {cg_levels(npts)}-level V(3,3) cycle (Richardson+Jacobi 0.8), "
+            f"to 1e-10 relative residual (BASELINE configs[2] / north-star time-to-solution)")
+
+
+CG_METRIC = "time to 1e-10 relative residual, MG-preconditioned CG (fp64)"
+
+
+def reference_arm_cg(a):
+    r = run_reference_opts(cg_options(a.npts))
+    n = a.npts - 2
+    ms = 1e3 * r["wall"]
+    sample = (f"the full solve: {r['iters']} CG iterations to 1e-10 at {a.npts}^2, KSPSolve bracket as the reference times it "
+              f"(src/solver.c:1958-1968); {r['kind']}: reference src/*.c over the in-repo mini-PETSc (real PETSc absent), OpenMP over "
+              f"{r['cores']} host threads")
+    save_record(f"cg_{a.npts}", {"host": os.uname().nodename, "npts": a.npts, "iters": r["iters"], "rnorm": r["rnorm"], "wall": r["wall"],
+                                 "cores": r["cores"], "kind": r["kind"], "sample": sample})
+    line = {"impl": "reference", "metric": CG_METRIC, "value": ms, "unit": "ms", "n_gpus": a.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cg_workload(a.npts), "unknowns": n * n}, "iterations": r["iters"],
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "rnorm": r["rnorm"][: r["iters"] + 1], "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def b200_arm_cg(a, mgb):
+    """Solve time to 1e-10 with the MG-preconditioned CG (cycle 8) at 1..8 GPUs, iteration count and residual history beside
+    the same-box CPU solve of the reference (src/solver.c:1884-1989)."""
+    import numpy as np
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank = 0
+    n = a.npts - 2
+    opts = cg_options(a.npts, extra="-mgb_csr 0")
+    if world > 1:
+        strips = importlib.import_module("multigrid-petsc_b200.strips")
+        s = strips.StripSession(opts)
+        rank = s.rank
+        import torch.distributed as dist
+    else:
+        s = mgb.Session(opts)
+    e = s.engine
+    jac = mgb.jacobi(0.8)
+    steps, warm = max(a.steps, 1), max(a.warmup, 3)
+
+    def solve():
+        return e.solve_pcmg(mgb.KSP_CG, jac, 3, coarse=mgb.COARSE_RICHARDSON, coarse_smoother=mgb.jacobi(1.0), coarse_its=1,
+                            rtol=1e-10, max_iter=100)
+    for _ in range(warm):
+        it, rn, reason, _ = solve()
+    l0 = e.launch_count()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    times = []
+    for _ in range(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        it, rn, reason, _ = solve()
+        torch.cuda.synchronize()
+        ms = e.last_solve_ms()
+        if world > 1:
+            ms = strips._max_over_ranks(ms)
+        times.append(ms)
+    launches = e.launch_count() - l0
+    t_end = time.time() + (0.0 if a.profile else 1.0)
+    k_busy = 0
+    while True:
+        go = 1.0 if time.time() < t_end else 0.0
+        if world > 1:
+            go = strips._max_over_ranks(go)
+        if go == 0.0 or k_busy > 200:
+            break
+        solve()
+        k_busy += 1
+    clocks = clk.stop() if rank == 0 else None
+    # fingerprint of the solution (partition independent); at N > 1 the per-rank checksums are combined on rank 0
+    r0, r1 = e.local_rows(0)
+    fsum, fxor = bits_fingerprint(e.get_vec(mgb.VEC_U, 0)[r0:r1])
+    if world > 1:
+        launches = strips._sum_over_ranks(launches)
+        parts = [None] * world
+        dist.all_gather_object(parts, (fsum, fxor))
+        fsum = sum(p[0] for p in parts) & 0xFFFFFFFFFFFFFFFF
+        fxor = 0
+        for p_ in parts:
+            fxor ^= p_[1]
+    s.close()
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+    ms = float(np.median(times))
+    # the CPU solve of the reference on this box: iterations and time (from the preceding --impl reference run, else run now)
+    rec = load_record(f"cg_{a.npts}")
+    if rec is None and not a.no_cpu_baseline and not a.profile:
+        r = run_reference_opts(cg_options(a.npts))
+        rec = {"host": os.uname().nodename, "npts": a.npts, "iters": r["iters"], "rnorm": r["rnorm"], "wall": r["wall"], "cores": r["cores"],
+               "kind": r["kind"], "sample": f"the full solve at {a.npts}^2 on {r['cores']} host threads, measured inside this run"}
+        save_record(f"cg_{a.npts}", rec)
+    line = {"metric": CG_METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cg_workload(a.npts), "unknowns": n * n, "parallelism": f"{world} row strip(s)",
+                       "l2": "inputs larger than L2" if 8.0 * n * n / world > 126e6 else "per-strip fine vectors fit L2; solves run back to back"},
+            "clocks": clocks, "iterations": it, "converged_reason": reason, "final_relative_residual": float(rn[-1]),
+            "ms_per_iteration": ms / max(it, 1), "ms_min": float(min(times)), "gpu_launches": int(launches),
+            "fingerprint": {"u_sum64": f"{fsum:#018x}", "u_xor64": f"{fxor:#018x}"}}
+    if rec:
+        k = min(len(rn), len(rec["rnorm"]))
+        # rnorm[] is normalised by rnorm[0]: an entry cannot be resolved below one fp64 epsilon of the initial residual (the
+        # recursively updated CG residual near 1e-11 differs by ~1e-20 absolute between summation orders): same rule as tests/
+        atol = 2.0 ** -52
+        diffs = [abs(float(rn[i]) - rec["rnorm"][i]) / abs(rec["rnorm"][i]) for i in range(k)]
+        hist_ok = all(abs(float(rn[i]) - rec["rnorm"][i]) <= PARITY_TOL * abs(rec["rnorm"][i]) + atol for i in range(k))
+        line["cpu_baseline"] = {"value": 1e3 * rec["wall"], "unit": "ms", "cores": rec["cores"], "kind": rec["kind"], "sample": rec["sample"],
+                                "iterations": rec["iters"]}
+        line["parity"] = {"against": "oracle/_ref/poisson_ref on this box, same input", "iterations_b200": it, "iterations_reference": rec["iters"],
+                          "iterations_equal": bool(it == rec["iters"]), "history_entries": k, "max_rel_diff": max(diffs), "tol": PARITY_TOL, "atol": atol,
+                          "ok": bool(it == rec["iters"] and hist_ok)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
     return 0
 
 
@@ -171,13 +412,15 @@ def b200_arm(a):
         raise SystemExit(f"bench.py: --gpus {a.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run --nproc-per-node {a.gpus}")
     torch.cuda.set_device(local)
     mgb = importlib.import_module("multigrid-petsc_b200")
+    if a.workload == "cg":
+        return b200_arm_cg(a, mgb)
     if a.workload == "weak":
         strips = importlib.import_module("multigrid-petsc_b200.strips")
         return strips.bench_weak(a, ClockSampler, hbm_peak)
     if world > 1:
         from importlib import import_module
         strips = import_module("multigrid-petsc_b200.strips")
-        return strips.bench_strips(a, NPTS, LEVELS, ClockSampler, hbm_peak, options)
+        return strips.bench_strips(a, NPTS, LEVELS, ClockSampler, hbm_peak, options, sys.modules[__name__])
 
     n = NPTS - 2
     steps, warm = a.steps, max(a.warmup, 3)
@@ -201,6 +444,7 @@ def b200_arm(a):
     clocks = clk.stop()
     assert it == steps, (it, steps)
     value = steps / (ms * 1e-3)
+    fp_sum, fp_xor = bits_fingerprint(e.get_vec(mgb.VEC_U, 0))       # the iterate after exactly `steps` cycles from u = 0
     peak, peak_kind = hbm_peak()
     # ---- roofline of the dominant kernel (fused down leg on the fine level), CUDA events on the engine's stream
     t_f = e.time_op("fused_down", 0, 20)
@@ -242,29 +486,24 @@ def b200_arm(a):
     e2e = cycles / t_e2e
     bytes_per_solve = 8 * n * n
     s.close()
-    # ---- CPU baseline on a bounded sample
-    cpu = None
-    if not a.no_cpu_baseline and not a.profile:
-        sn, sl, sc = 4097, 12, 3
-        v, cores, kind, wall, done = run_reference(sn, sl, sc)
-        scale = ((sn - 2) ** 2) / float(n * n)
-        cpu = {"value": v * scale, "unit": "V-cycles/s", "cores": cores, "kind": kind,
-               "sample": (f"{done} V-cycles at {sn}^2 / {sl} levels ({wall:.2f} s of cycle loop; {v:.3f} cycles/s there), scaled by the "
-                          f"unknown ratio {scale:.4f} to {NPTS}^2; {kind} = reference src/*.c over the in-repo mini-PETSc, "
-                          f"OpenMP on {cores} host threads; `--impl reference` runs the full size")}
-    line = {"metric": "V-cycles/sec (fp64, 8193^2 grid)", "value": value, "unit": "V-cycles/s", "n_gpus": 1, "steps": steps,
+    # ---- CPU baseline + parity at the full size: the reference binary's first cycles on the same 8193^2 input
+    cpu, rec = cpu_block(a)
+    traffic, traffic_src = ncu_traffic()
+    line = {"metric": METRIC, "value": value, "unit": "V-cycles/s", "n_gpus": 1, "steps": steps,
             "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"2D Poisson {NPTS}^2 fp64, {LEVELS}-level V(3,3), Richardson+Jacobi 0.8 (BASELINE configs[3] at N=1)",
+            "config": {"workload": WORKLOAD,
                        "unknowns": n * n, "l2": "inputs larger than L2 (537 MB per fine vector)", "parallelism": "1 strip"},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_jfused<3,PRE_GIVEN,POST_RESTRICT> level 0 (3 Jacobi sweeps + residual + restriction, one pass)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
-                         "traffic": NCU_TRAFFIC_FUSED_DOWN, "algorithmic_bytes_per_launch": FUSED_DOWN_BYTES_PER_UNKNOWN * n * n,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": FUSED_DOWN_BYTES_PER_UNKNOWN * n * n,
+                         "limiter": "HBM is the roofline this fraction is quoted against, but not the limiter: ncu shows DRAM ~63 % busy, the "
+                                    "L1/shared-memory data pipe ~71 %, fp64 pipe ~39 %, issue slots ~50 % at 4 warps per scheduler",
                          "note": "temporal blocking: the kernel's own compulsory traffic is 26 B/unknown; by the unfused SURVEY 8d count "
                                  "(90 B/unknown for the 3 sweeps + residual + restriction it replaces) it delivers "
-                                 f"{FUSED_DOWN_UNFUSED_BYTES * n * n / (t_f * 1e-3) / 1e9:.0f} GB/s-equivalent; it is fp64-issue / shared-memory bound, "
-                                 "not HBM bound (DESIGN.md section 4). The one-sweep kernels it replaces are listed in fine_level_ops.",
+                                 f"{FUSED_DOWN_UNFUSED_BYTES * n * n / (t_f * 1e-3) / 1e9:.0f} GB/s-equivalent "
+                                 "(DESIGN.md section 4). The one-sweep kernels it replaces are listed in fine_level_ops.",
                          "vcycle_gbs_unfused_count": VCYCLE_BYTES_PER_FINE_UNKNOWN * n * n * value / 1e9,
                          "fine_level_ops": per_op},
             "e2e": {"value": e2e, "unit": "V-cycles/s", "h2d_bytes_per_step": bytes_per_solve * nstream / cycles,
@@ -275,9 +514,14 @@ def b200_arm(a):
                             "one; wall clock over the whole batch incl. the un-overlapped first upload and last download; bytes are per "
                             "V-cycle. single_solve_value = the same without overlap (one pb200_solve_rhs at a time)"},
             "gpu_launches": launches,
-            "final_relative_residual": float(rn[-1])}
+            "final_relative_residual": float(rn[-1]),
+            "fingerprint": {"cycles": steps, "u_sum64": f"{fp_sum:#018x}", "u_xor64": f"{fp_xor:#018x}",
+                            "note": "sum and xor of the 64-bit patterns of the fine-level iterate after `steps` cycles from u = 0: "
+                                    "independent of the strip partition, identical at every N when the strips are bit-identical"}}
     if cpu:
         line["cpu_baseline"] = cpu
+    if rec:
+        line["parity"] = parity_block(rn, rec)
     print(json.dumps(line))
     return 0
 
@@ -289,8 +533,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="strong", choices=["strong", "weak"],
-                    help="strong (default): 8193^2 split over the GPUs (BASELINE configs[3]); weak: 4096 x 4097 points per GPU (configs[4])")
+    ap.add_argument("--workload", default="strong", choices=["strong", "weak", "cg"],
+                    help="strong (default): 8193^2 split over the GPUs (BASELINE configs[3]); weak: 4096 x 4097 points per GPU (configs[4]); "
+                         "cg: MG-preconditioned CG to 1e-10 (configs[2] and the north-star time-to-solution), --npts 4097|8193")
+    ap.add_argument("--npts", type=int, default=8193, help="grid points per side for --workload cg")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no busy loop, one e2e solve, no CPU baseline")
     a = ap.parse_args()
     if a.impl == "reference":

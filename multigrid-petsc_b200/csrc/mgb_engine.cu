@@ -36,6 +36,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -108,7 +109,7 @@ struct Strip {
 	double *partial = nullptr; size_t partial_cap = 0;
 	double *scal = nullptr, *scal_host = nullptr, *scal_host_dev = nullptr;   // device scalars, mapped pinned mirror (+ its device alias)
 	double *tab_x = nullptr, *tab_y = nullptr;
-	int *status_host = nullptr;
+	int *status_host = nullptr, *status_host_dev = nullptr;   // mapped pinned: a timed-out wait is visible to the host without a copy
 	double *stage_in = nullptr, *stage_out = nullptr;     // dense staging buffers for PCIe copies of large vectors (lazy)
 	size_t stage_cap = 0;
 	cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host <-> device copies overlapped with a solve (mgb_solve_vcycle_many)
@@ -139,6 +140,9 @@ struct mgb_engine {
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
 	int coarse_threshold = 63;               // levels with at most this many rows run in the persistent bottom kernel
 	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
+	int bcast_done = -1;                     // level whose result a fused leg has just broadcast from inside the kernel
+	bool dead = false;                       // a ghost-row wait timed out: the ranks' version counters are out of step, the engine is unusable
+	bool inkernel = true;                    // fused legs push / wait for their strip-to-strip rows themselves (MGB_INKERNEL_HALO=0: separate k_xfer launches)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
 static void drop_graphs(mgb_engine *e);
@@ -291,25 +295,12 @@ extern "C" int mgb_destroy(mgb_engine *e)
 	return MGB_OK;
 }
 
-extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
+// everything of mgb_create that can fail after the engine object exists (the caller destroys it on failure)
+static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 {
-	if (!cfg || !out) return fail(MGB_EINVAL, "null argument");
-	if (cfg->levels < 1 || cfg->ni < 1 || cfg->nj < 1) return fail(MGB_EINVAL, "levels, ni, nj must be positive");
-	if (cfg->levels > MGB_MAXL) return fail(MGB_EINVAL, "at most %d levels", MGB_MAXL);
-	const int P = cfg->nranks < 1 ? 1 : cfg->nranks;
-	if (P > MGB_MAX_RANKS) return fail(MGB_EINVAL, "at most %d ranks (one NVSwitch domain)", MGB_MAX_RANKS);
-	if (cfg->rank < 0 || cfg->rank >= P) return fail(MGB_EINVAL, "rank %d out of range", cfg->rank);
-	int ndev = 0;
-	cudaError_t ce = cudaGetDeviceCount(&ndev);
-	if (ce != cudaSuccess || ndev < 1)
-		return fail(MGB_ECUDA, "no CUDA device available (%s): the B200 engine has no CPU fallback", cudaGetErrorString(ce));
-	if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
-	int dev = 0; CU(cudaGetDevice(&dev));
-	mgb_engine *e = new mgb_engine();
 	e->cfg = *cfg; e->cfg.nranks = P;
 	e->P = P; e->L = cfg->levels;
-	int rc = build_geometry(&e->cfg, e->geo, &e->La);
-	if (rc) { delete e; return rc; }
+	TRY(build_geometry(&e->cfg, e->geo, &e->La));
 	e->lay.resize(P);
 	for (int r = 0; r < P; ++r) build_layout(&e->cfg, e->geo, e->La, r, e->lay[r]);
 	const int nlocal = (P > 1 && cfg->emulate) ? P : 1;
@@ -354,13 +345,36 @@ extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
 		CU(cudaMemsetAsync(s.scal, 0, sizeof(double) * 64, s.stream));
 		CU(cudaHostAlloc(&s.scal_host, sizeof(double) * 64, cudaHostAllocMapped));
 		CU(cudaHostGetDevicePointer(&s.scal_host_dev, s.scal_host, 0));
-		CU(cudaMallocHost(&s.status_host, sizeof(int) * 4));
+		CU(cudaHostAlloc(&s.status_host, sizeof(int) * 4, cudaHostAllocMapped));
 		s.status_host[0] = 0;
+		CU(cudaHostGetDevicePointer(&s.status_host_dev, s.status_host, 0));
 		CU(cudaMalloc(&s.tab_x, sizeof(double) * (size_t)(cfg->nj + 16)));
 		CU(cudaMalloc(&s.tab_y, sizeof(double) * (size_t)(cfg->ni + 16)));
 	}
 	CU(cudaStreamSynchronize(e->strips[0].stream));
 	e->connected = (P == 1) || nlocal > 1;
+	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
+	return MGB_OK;
+}
+
+
+extern "C" int mgb_create(const mgb_config *cfg, mgb_engine **out)
+{
+	if (!cfg || !out) return fail(MGB_EINVAL, "null argument");
+	if (cfg->levels < 1 || cfg->ni < 1 || cfg->nj < 1) return fail(MGB_EINVAL, "levels, ni, nj must be positive");
+	if (cfg->levels > MGB_MAXL) return fail(MGB_EINVAL, "at most %d levels", MGB_MAXL);
+	const int P = cfg->nranks < 1 ? 1 : cfg->nranks;
+	if (P > MGB_MAX_RANKS) return fail(MGB_EINVAL, "at most %d ranks (one NVSwitch domain)", MGB_MAX_RANKS);
+	if (cfg->rank < 0 || cfg->rank >= P) return fail(MGB_EINVAL, "rank %d out of range", cfg->rank);
+	int ndev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev < 1)
+		return fail(MGB_ECUDA, "no CUDA device available (%s): the B200 engine has no CPU fallback", cudaGetErrorString(ce));
+	if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
+	int dev = 0; CU(cudaGetDevice(&dev));
+	mgb_engine *e = new mgb_engine();
+	const int rc = create_body(e, cfg, P, dev);
+	if (rc != MGB_OK) { mgb_destroy(e); return rc; }     // g_err keeps the message of the failing call
 	*out = e;
 	return MGB_OK;
 }
@@ -431,9 +445,23 @@ static int check_status(mgb_engine *e)
 	for (auto &s : e->strips) {
 		CU(cudaMemcpyAsync(s.status_host, status_of(e, s), sizeof(int), cudaMemcpyDeviceToHost, s.stream));
 		CU(cudaStreamSynchronize(s.stream));
-		if (s.status_host[0] != 0)
+		if (s.status_host[0] != 0) {
+			e->dead = true;
 			return fail(MGB_ECUDA, "rank %d: timed out waiting for a neighbour's ghost rows (a peer stopped or the ranks diverged)", s.rank);
+		}
 	}
+	return MGB_OK;
+}
+// after any synchronisation, without a copy: the mapped host mirror of the status word (set by a timed-out wait)
+static int quick_status(mgb_engine *e)
+{
+	if (e->P == 1) return MGB_OK;
+	for (auto &s : e->strips)
+		if (s.status_host && s.status_host[0] != 0) {
+			e->dead = true;
+			return fail(MGB_ECUDA, "rank %d: timed out waiting for a neighbour's rows (a peer stopped or the ranks diverged); the engine must be "
+			            "destroyed on every rank", s.rank);
+		}
 	return MGB_OK;
 }
 static int flush_all(mgb_engine *e);
@@ -463,7 +491,7 @@ extern "C" int mgb_set_level_operator(mgb_engine *e, int level, const double *ro
 			g.uniform = 2;
 	}
 	g.coef_set = true;
-	e->sor_omega = 1.0;
+	e->sor_omega = -1.0;          // idiag of this level is now 1/diag whatever omega the others hold: recompute all on the next SOR use
 	e->csr_built = false;
 	drop_graphs(e);
 	for (auto &s : e->strips) {
@@ -536,7 +564,7 @@ static int xfer_run(mgb_engine *e, std::vector<XferArgs> &args, const std::vecto
 {
 	for (size_t i = 0; i < e->strips.size(); ++i) {
 		Strip &s = e->strips[i]; XferArgs &a = args[i];
-		a.ver = ver_of(e, s) + chan; a.ticket = ticket_of(e, s) + chan; a.status = status_of(e, s); a.spin_limit = e->spin_limit;
+		a.ver = ver_of(e, s) + chan; a.ticket = ticket_of(e, s) + chan; a.status = status_of(e, s); a.status_host = s.status_host_dev; a.spin_limit = e->spin_limit;
 		a.do_push = 1; a.do_wait = e->strips.size() == 1 ? 1 : 0;
 		k_xfer<<<xfer_blocks(tot[i]), MGB_XFER_THREADS, 0, s.stream>>>(a);
 		LAUNCHED(e); KCHECK();
@@ -1054,7 +1082,7 @@ static int read_scalars(mgb_engine *e, int first, int count)
 	k_publish<<<1, 32, 0, s.stream>>>(s.scal_host_dev, s.scal, first, count);
 	LAUNCHED(e); KCHECK();
 	CU(cudaStreamSynchronize(s.stream));
-	return MGB_OK;
+	return quick_status(e);
 }
 static double *host_scal(mgb_engine *e) { return e->strips[0].scal_host; }
 
@@ -1233,8 +1261,19 @@ static LevelDev fused_ldev(const mgb_engine *e, const Strip &s, int l)
 template <int D, int PRE, int POST>
 static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st)
 {
-	static bool optin = false;                 // > 48 KB of dynamic shared memory needs the opt-in once per kernel
-	if (!optin) { cudaFuncSetAttribute(k_jfused<D, PRE, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jf_smem_bytes<D>()); optin = true; }
+	// > 48 KB of dynamic shared memory needs the opt-in once per kernel AND per device (a function attribute lives in
+	// the device's context): one flag per device, set under a lock
+	static std::mutex mu;
+	static bool optin[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (dev >= 0 && dev < 64 && !optin[dev]) {
+			if (cudaFuncSetAttribute(k_jfused<D, PRE, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jf_smem_bytes<D>()) == cudaSuccess)
+				optin[dev] = true;                 // on failure the launch below reports the error through KCHECK
+		}
+	}
 	k_jfused<D, PRE, POST><<<grid, FJ_THREADS, jf_smem_bytes<D>(), st>>>(a);
 }
 
@@ -1293,7 +1332,131 @@ static bool fusable(const mgb_engine *e, const mgb_smoother *sm) { return sm->ty
 // One leg on level l: [x += pro * u[l+1]] -> `its` Jacobi sweeps on (b = bv, x = xv) -> [b[l+1] = res * (b - A x)] or
 // [scal[norm_slot] = ||b - A x||].  Sweeps beyond FJ_MAXD are chained as extra passes.  On return the iterate is in v[xv]
 // with valid ghost rows; a restricted right-hand side has been exchanged / gathered.
-static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int pre, int post, int bv, int xv, int sv, int norm_slot)
+// ---- strip-to-strip traffic of a fused leg, done inside k_jfused (FusedComm, mgb_fused.cuh)
+static unsigned long long *flag_at(mgb_engine *e, int dst_rank, int chan, int src_rank) { return flags_of(e, dst_rank) + (size_t)chan * MGB_MAX_RANKS + src_rank; }
+static void add_wait(FusedComm &X, int which, int &n, mgb_engine *e, const Strip &s, int chan, int src_rank)
+{
+	if (n >= FJ_MAXWAIT) return;
+	X.w_flag[which][n] = flag_at(e, s.rank, chan, src_rank);
+	X.w_ver[which][n] = ver_of(e, s) + chan;
+	++n;
+}
+// Fill a.X for strip s.  out_phys: physical buffer of u_out; bcast_out: level l is the first agglomerated one and its
+// result feeds the prolongation of every rank.  Returns through a.bc a pointer into rank 0's HBM when the restricted
+// right-hand side is gathered there.
+static void fused_comm(mgb_engine *e, Strip &s, int l, int D, int pre_k, int post_k, int bv, int xv, int out_phys, bool bcast_out,
+                       dim3 grid, FusedArgs &a)
+{
+	FusedComm &X = a.X;
+	const int r = s.rank, P = e->P;
+	const LevelGeom &g = e->geo[l];
+	X.status = status_of(e, s); X.status_host = s.status_host_dev; X.spin_limit = e->spin_limit;
+	const bool prolong = pre_k == PRE_PROLONG || pre_k == PRE_PROLONG_MULTADD;
+	int first_chan = -1;
+	auto channel = [&](int chan) -> int { const int c = X.nch++; X.ver[c] = ver_of(e, s) + chan; X.nsig[c] = 0; if (first_chan < 0) first_chan = chan; return c; };
+	if (g.dist) {
+		const size_t pitch = g.pitch;
+		const int ni = e->lay[r].ni[l];
+		// ghost rows this leg reads
+		if (pre_k != PRE_ZERO) {
+			const int ch = CH_HALO(l, s.lev[l].phys[xv]);
+			if (r > 0) add_wait(X, 0, X.nw_top, e, s, ch, r - 1);
+			if (r < P - 1) add_wait(X, 1, X.nw_bot, e, s, ch, r + 1);
+		}
+		{
+			const int ch = CH_HALO(l, s.lev[l].phys[bv]);
+			if (r > 0) add_wait(X, 0, X.nw_top, e, s, ch, r - 1);
+			if (r < P - 1) add_wait(X, 1, X.nw_bot, e, s, ch, r + 1);
+		}
+		if (prolong) {
+			if (e->geo[l + 1].dist) {
+				const int ch = CH_HALO(l + 1, s.lev[l + 1].phys[MGB_VEC_U]);
+				if (r > 0) add_wait(X, 0, X.nw_top, e, s, ch, r - 1);
+				if (r < P - 1) add_wait(X, 1, X.nw_bot, e, s, ch, r + 1);
+			} else if (r != 0) add_wait(X, 2, X.nw_all, e, s, CH_BCAST(l + 1), 0);
+		}
+		// ghost rows of u_out pushed to the neighbours
+		if (D > 0) {
+			const int ch = CH_HALO(l, out_phys), c = channel(ch);
+			X.pu[X.npu++] = {r > 0 ? peer_vec(e, r - 1, l, out_phys) + (size_t)e->lay[r - 1].ni[l] * pitch : nullptr, 0, HALO_DEPTH};
+			X.pu[X.npu++] = {r < P - 1 ? peer_vec(e, r + 1, l, out_phys) - (size_t)ni * pitch : nullptr, ni - HALO_DEPTH, ni};
+			if (r > 0) X.sig[c][X.nsig[c]++] = flag_at(e, r - 1, ch, r);
+			if (r < P - 1) X.sig[c][X.nsig[c]++] = flag_at(e, r + 1, ch, r);
+		}
+		if (post_k == POST_RESTRICT) {
+			const LevelGeom &gc = e->geo[l + 1];
+			const int kB = s.lev[l + 1].phys[MGB_VEC_B];
+			if (gc.dist) {
+				const int ch = CH_HALO(l + 1, kB), c = channel(ch);
+				const int nic = e->lay[r].ni[l + 1];
+				X.pb[X.npb++] = {r > 0 ? peer_vec(e, r - 1, l + 1, kB) + (size_t)e->lay[r - 1].ni[l + 1] * gc.pitch : nullptr, 0, HALO_DEPTH};
+				X.pb[X.npb++] = {r < P - 1 ? peer_vec(e, r + 1, l + 1, kB) - (size_t)nic * gc.pitch : nullptr, nic - HALO_DEPTH, nic};
+				if (r > 0) X.sig[c][X.nsig[c]++] = flag_at(e, r - 1, ch, r);
+				if (r < P - 1) X.sig[c][X.nsig[c]++] = flag_at(e, r + 1, ch, r);
+			} else {
+				// gather: this rank's coarse rows go straight into rank 0's copy of the first agglomerated level
+				const int ch = CH_GATHER(l + 1), c = channel(ch);
+				a.bc = peer_vec(e, 0, l + 1, kB) + (size_t)gc.rows[r] * gc.pitch;
+				X.bc_remote = 1;
+				if (r != 0) X.sig[c][X.nsig[c]++] = flag_at(e, 0, ch, r);
+			}
+		}
+	} else if (P > 1 && l == e->La && r == 0) {
+		// the first agglomerated level on rank 0: its right-hand side was gathered, its result may be broadcast
+		if (pre_k == PRE_ZERO) for (int t = 1; t < P; ++t) add_wait(X, 2, X.nw_all, e, s, CH_GATHER(l), t);
+		if (bcast_out && D > 0) {
+			const int ch = CH_BCAST(l), c = channel(ch);
+			for (int t = 1; t < P && X.npu < FJ_MAXPUSH; ++t) {
+				int c0 = g.rows[t] - 3, c1 = g.rows[t + 1] + 3;               // the fused up leg reads 3 coarse ghost rows
+				if (c0 < 0) c0 = 0;
+				if (c1 > g.gni) c1 = g.gni;
+				X.pu[X.npu++] = {peer_vec(e, t, l, out_phys), c0, c1};
+				X.sig[c][X.nsig[c]++] = flag_at(e, t, ch, 0);
+			}
+		}
+	}
+	// blocks that take a ticket: the row chunks that intersect a push range (all of them when bc is remote), times the column tiles
+	if (X.nch) {
+		int chunks = 0;
+		const int ni = s.lev[l].ni;
+		for (int y0 = 0; y0 < ni; y0 += a.rows) {
+			const int y1 = y0 + a.rows < ni ? y0 + a.rows : ni;
+			bool takes = X.bc_remote && post_k == POST_RESTRICT;
+			for (int k = 0; k < X.npu; ++k) takes |= (D > 0 && y0 < X.pu[k].hi && y1 > X.pu[k].lo);
+			for (int k = 0; k < X.npb; ++k) takes |= (post_k == POST_RESTRICT && (y0 >> 1) < X.pb[k].hi && (y1 >> 1) > X.pb[k].lo);
+			chunks += takes ? 1 : 0;
+		}
+		X.npushblocks = chunks * (int)grid.x;
+		X.ticket = ticket_of(e, s) + first_chan;
+		if (X.npushblocks == 0) X.nch = 0;
+	}
+}
+// rank 0 consumes a gathered right-hand side in a kernel that cannot wait by itself (the persistent bottom kernel)
+static int wait_gather(mgb_engine *e, int l)
+{
+	if (e->P == 1) return MGB_OK;
+	for (auto &s : e->strips) {
+		if (s.rank != 0) continue;
+		XferArgs a; memset(&a, 0, sizeof a);
+		const int chan = CH_GATHER(l);
+		a.ver = ver_of(e, s) + chan; a.ticket = ticket_of(e, s) + chan; a.status = status_of(e, s); a.status_host = s.status_host_dev;
+		a.spin_limit = e->spin_limit; a.do_push = 0; a.do_wait = 1;
+		for (int t = 1; t < e->P; ++t) a.wait_flag[a.nwait++] = flag_at(e, 0, chan, t);
+		k_xfer<<<1, 32, 0, s.stream>>>(a);
+		LAUNCHED(e); KCHECK();
+	}
+	return MGB_OK;
+}
+
+// before a prolongation from the first agglomerated level lc onto distributed strips: its rows must reach every rank
+static int need_bcast(mgb_engine *e, int lc)
+{
+	if (e->bcast_done == lc) { e->bcast_done = -1; return MGB_OK; }     // they travelled inside the fused leg that produced them
+	return bcast_rows(e, lc, MGB_VEC_U);
+}
+
+static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int pre, int post, int bv, int xv, int sv, int norm_slot,
+                     bool bcast_out = false)
 {
 	const LevelGeom &g = e->geo[l];
 	if (its < 1) return fail(MGB_EINVAL, "fused leg needs at least one sweep");
@@ -1304,8 +1467,15 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 		const int pre_k = firstc ? pre : PRE_GIVEN, post_k = lastc ? post : POST_NONE;
 		std::vector<int> nb;
 		TRY(flush_levels(e, l, (pre_k == PRE_PROLONG || pre_k == PRE_PROLONG_MULTADD) ? l + 1 : l));
+		const bool inkernel = e->P > 1 && e->inkernel;     // ghost rows / gather / broadcast travel inside k_jfused
+		const bool bcast_k = bcast_out && lastc && inkernel && !g.dist && l == e->La;
+		if (bcast_k) e->bcast_done = l;
 		for (auto &s : e->strips) {
-			if (!computes(s, l)) continue;
+			if (!computes(s, l)) {
+				// the ranks that do not compute on a broadcast level keep their version counter of the channel in step
+				if (bcast_k) { k_bump<<<1, 1, 0, s.stream>>>(ver_of(e, s) + CH_BCAST(l)); LAUNCHED(e); KCHECK(); }
+				continue;
+			}
 			SLevel &S = s.lev[l];
 			FusedArgs a; memset(&a, 0, sizeof a);
 			a.u_in = S.v[xv]; a.b = S.v[bv]; a.u_out = S.v[sv];
@@ -1329,6 +1499,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 				a.partial = s.partial;
 				nb.push_back((int)(grid.x * grid.y));
 			}
+			if (inkernel) fused_comm(e, s, l, D, pre_k, post_k, bv, xv, S.phys[sv], bcast_k, grid, a);
 			int rc;
 			switch (D) {
 			case 1: rc = dispatch_jfused<1>(pre_k, post_k, a, grid, s.stream); break;
@@ -1339,10 +1510,12 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			LAUNCHED(e); KCHECK();
 		}
 		swap_vec(e, l, xv, sv);
-		TRY(halo(e, l, xv, HALO_DEPTH));
-		if (post_k == POST_RESTRICT) {
-			if (e->geo[l + 1].dist) TRY(halo(e, l + 1, MGB_VEC_B, HALO_DEPTH));
-			else if (g.dist) TRY(gather_rows(e, l + 1, MGB_VEC_B));
+		if (!inkernel) {
+			TRY(halo(e, l, xv, HALO_DEPTH));
+			if (post_k == POST_RESTRICT) {
+				if (e->geo[l + 1].dist) TRY(halo(e, l + 1, MGB_VEC_B, HALO_DEPTH));
+				else if (g.dist) TRY(gather_rows(e, l + 1, MGB_VEC_B));
+			}
 		}
 		if (post_k == POST_NORM) TRY(reduce_tail(e, l, nb, norm_slot, 1));
 		done += D;
@@ -1546,11 +1719,13 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));      // :1531-1535
 			for (int l = 1; l < Lc - 1 && l < lp; ++l)
 				TRY(fused_leg(e, l, s, p->v0, PRE_ZERO, POST_RESTRICT, B, U, W, 0));                     // :1534-1536
-			if (lp < Lc) TRY(bottom_cycle(e, lp, p->v0, s->scale, p->v1, s->scale, false));
-			else TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0));                    // :1536 coarsest
+			if (lp < Lc) {
+				if (lp == e->La && e->inkernel) TRY(wait_gather(e, lp));   // the bottom kernel consumes the gathered right-hand side
+				TRY(bottom_cycle(e, lp, p->v0, s->scale, p->v1, s->scale, false));
+			} else TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0, true));             // :1536 coarsest
 			for (int l = (lp < Lc ? lp - 1 : Lc - 2); l >= 0; --l) {
-				if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(bcast_rows(e, l + 1, U));
-				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0));  // :1540-1546
+				if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(need_bcast(e, l + 1));
+				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0, true));  // :1540-1546
 			}
 		}
 		TRY(flush_all(e));
@@ -1638,13 +1813,20 @@ static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm
 				cudaGraph_t graph;
 				const long long l0 = e->launches;
 				CU(cudaStreamBeginCapture(s0.stream, cudaStreamCaptureModeThreadLocal));
+				std::vector<PtrState> before; save_state(e, before);
+				graph = nullptr;
 				int r = vcycle_body(e, p, false);
-				cudaError_t ce = cudaStreamEndCapture(s0.stream, &graph);
-				if (r != MGB_OK) return r;
-				if (ce != cudaSuccess) return fail(MGB_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+				cudaError_t ce = cudaStreamEndCapture(s0.stream, &graph);     // always ends the capture, also after a failed body
+				if (r != MGB_OK || ce != cudaSuccess) {
+					if (graph) cudaGraphDestroy(graph);
+					load_state(e, before); e->launches = l0; e->pending.clear();
+					if (r != MGB_OK) return r;
+					return fail(MGB_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+				}
 				GraphEntry ne; ne.key = key; ne.exec = nullptr;
-				CU(cudaGraphInstantiate(&ne.exec, graph, 0));
+				ce = cudaGraphInstantiate(&ne.exec, graph, 0);
 				cudaGraphDestroy(graph);
+				if (ce != cudaSuccess) { load_state(e, before); e->launches = l0; return fail(MGB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
 				ne.launches = e->launches - l0;
 				e->launches = l0;
 				save_state(e, ne.after);
@@ -1657,6 +1839,7 @@ static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm
 			e->launches += g->launches;
 		}
 		CU(cudaStreamSynchronize(s0.stream));
+		TRY(quick_status(e));
 		rn = s0.scal_host[0];
 		iter = iter + 1;
 		rnorm[iter] = rn;
@@ -1669,7 +1852,8 @@ static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm
 
 static int vcycle_check(mgb_engine *e, const mgb_vcycle_params *p)
 {
-	TRY(require_ops(e, true)); TRY(check_smoother(e, &p->smoother));
+	TRY(require_ops(e, true));
+	if (e->dead) return fail(MGB_ESTATE, "the engine is unusable after a timed-out strip exchange: destroy it on every rank"); TRY(check_smoother(e, &p->smoother));
 	if (p->v0 < 0 || p->v1 < 0 || p->max_iter < 0) return fail(MGB_EINVAL, "negative sweep or iteration count");
 	return MGB_OK;
 }
@@ -1750,6 +1934,9 @@ extern "C" int mgb_solve_vcycle_many(mgb_engine *e, const mgb_vcycle_params *p, 
 static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, int xv)
 {
 	const int Lc = e->L;
+	// the gathered right-hand side of the first agglomerated level: the fused legs wait for it themselves, every other consumer
+	// (bottom kernel, LU, one-sweep kernels) gets a wait launch on rank 0 (harmless when a fused leg follows)
+	if (e->P > 1 && e->inkernel && l == e->La && l >= 1) TRY(wait_gather(e, l));
 	if (l >= 1 && !p->no_fuse && !p->no_bottom && p->coarse == MGB_COARSE_RICHARDSON && fusable(e, &p->level_smoother) &&
 	    fusable(e, &p->coarse_smoother) && p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e) &&
 	    bv == MGB_VEC_B && xv == MGB_VEC_U)
@@ -1757,7 +1944,7 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 	if (l == Lc - 1) {
 		if (p->coarse == MGB_COARSE_RICHARDSON) {
 			if (!p->no_fuse && fusable(e, &p->coarse_smoother) && p->coarse_its >= 1)
-				return fused_leg(e, l, &p->coarse_smoother, p->coarse_its, PRE_ZERO, POST_NONE, bv, xv, MGB_VEC_W, 0);
+				return fused_leg(e, l, &p->coarse_smoother, p->coarse_its, PRE_ZERO, POST_NONE, bv, xv, MGB_VEC_W, 0, true);
 			return smooth(e, l, &p->coarse_smoother, p->coarse_its, true, bv, xv, MGB_VEC_W);
 		}
 		TRY(flush_levels(e, l, l));
@@ -1772,8 +1959,8 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 	if (!p->no_fuse && fusable(e, &p->level_smoother) && p->level_its >= 1) {
 		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_ZERO, POST_RESTRICT, bv, xv, MGB_VEC_W, 0));
 		TRY(pcmg_cycle(e, p, l + 1, MGB_VEC_B, MGB_VEC_U));
-		if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(bcast_rows(e, l + 1, MGB_VEC_U));
-		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_PROLONG_MULTADD, POST_NONE, bv, xv, MGB_VEC_W, 0));
+		if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(need_bcast(e, l + 1));
+		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_PROLONG_MULTADD, POST_NONE, bv, xv, MGB_VEC_W, 0, true));
 		return MGB_OK;
 	}
 	TRY(smooth(e, l, &p->level_smoother, p->level_its, true, bv, xv, MGB_VEC_W));     // pre-smooth from x = 0
@@ -1788,7 +1975,7 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 static int ksp_converged(const mgb_pcmg_params *p, int it, double rn, double *rnorm0, double *ttol)
 {
 	if (it == 0) { *rnorm0 = rn; *ttol = fmax(p->rtol * rn, p->abstol); }
-	if (rn != rn) return -4;                       // KSP_DIVERGED_DTOL (nan)
+	if (rn != rn || rn - rn != 0.0) return -9;     // KSP_DIVERGED_NANORINF
 	if (rn <= *ttol) return (rn < p->abstol) ? 3 : 2;
 	if (rn >= p->dtol * (*rnorm0)) return -4;
 	return 0;
@@ -1799,6 +1986,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 	NEED(e);
 	if (!p || !rnorm || !num_iter) return fail(MGB_EINVAL, "null argument");
 	TRY(require_ops(e, true));
+	if (e->dead) return fail(MGB_ESTATE, "the engine is unusable after a timed-out strip exchange: destroy it on every rank");
 	const int Lc = e->L;
 	if (Lc < 2) return fail(MGB_EINVAL, "cycle 8 needs at least two levels");
 	TRY(check_smoother(e, &p->level_smoother));

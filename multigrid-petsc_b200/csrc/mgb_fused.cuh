@@ -28,6 +28,7 @@
 #pragma once
 #include "mgb_common.cuh"
 #include "mgb_transfer.cuh"
+#include "mgb_halo.cuh"
 
 #define FJ_THREADS 128
 #define FJ_COLS (2 * FJ_THREADS)
@@ -81,6 +82,32 @@ __device__ __forceinline__ void bulk_g2s(unsigned smem, const void *gmem, unsign
 enum { PRE_GIVEN = 0, PRE_ZERO = 1, PRE_PROLONG = 2, PRE_PROLONG_MULTADD = 3 };
 enum { POST_NONE = 0, POST_RESTRICT = 1, POST_NORM = 2 };
 
+// Strip-to-strip traffic done BY the fused kernel (no separate exchange launch; protocol notes in mgb_halo.cuh):
+//   push   finished rows of u_out / of the coarse right-hand side that lie in a push range are also stored into a peer's
+//          HBM (its ghost rows, or rank 0's whole level for the gather / every rank's staging rows for the broadcast);
+//   signal the last of the pushing blocks (ticket) fences and raises the version flags in the destinations' memory;
+//   wait   blocks that read ghost rows (the first / last row chunks) or a gathered / broadcast level (all blocks) spin on
+//          their own flag words until the peers' pushes of the current version have landed; other blocks never wait.
+#define FJ_MAXPUSH 8
+#define FJ_MAXWAIT 8
+struct PushEnt { double *dst; int lo, hi; };   // rows [lo, hi) of the output -> dst[row * pitch + col] (dst may be null: no neighbour)
+struct FusedComm {
+	int npu, npb;                               // push ranges of u_out (fine rows) / bc (coarse rows)
+	PushEnt pu[FJ_MAXPUSH], pb[2];
+	int bc_remote;                              // 1: A.bc itself points into a peer's HBM (gather): every block that writes bc signals
+	int nch;                                    // channels signalled by this kernel (0..2)
+	unsigned long long *ver[2];                 // my version counter of each channel
+	int nsig[2];
+	unsigned long long *sig[2][FJ_MAXPUSH];     // flag words in the destinations' memory
+	unsigned int *ticket;                       // zero between launches
+	int npushblocks;                            // blocks of this launch that take a ticket
+	int nw_top, nw_bot, nw_all;                 // waits of the blocks reading ghost rows above / below, and of every block
+	const unsigned long long *w_flag[3][FJ_MAXWAIT];
+	const unsigned long long *w_ver[3][FJ_MAXWAIT];
+	int *status, *status_host;                  // != 0 after a timed-out wait (device word; mapped host mirror)
+	long long spin_limit;
+};
+
 struct FusedArgs {
 	const double *u_in;      // stage 0 (unused for PRE_ZERO)
 	const double *b;
@@ -93,6 +120,7 @@ struct FusedArgs {
 	double scale;
 	int rows;                // rows per block (even)
 	int gni;                 // global number of rows of the fine level
+	FusedComm X;             // all zero on a single strip
 };
 
 struct Coef { double aS, aW, aC, aE, aN, dinv, nS; };   // nS = -aS (power-of-two path)
@@ -161,6 +189,7 @@ struct JfBlock {
 	int tid, c0, j0, y0, y1;
 	ptrdiff_t P;
 	bool in0, in1, ld_ok, st_ok;
+	bool push_u, push_b;     // this block's rows intersect a push range of u_out / of the coarse right-hand side
 	bool tma;                // input rows arrive by TMA bulk copies (pitch >= FJ_COLS) instead of per-thread cp.async
 	int rbase;               // first row of the input rings: row i lives in slot (i - rbase) & (FJ_NR - 1)
 	unsigned long long *bar; // FJ_NR mbarriers, one per ring slot (TMA path)
@@ -314,7 +343,14 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	// ---- the finished row t-D
 	{
 		const int c = t - D;
-		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);   // D = 0: u is unchanged
+		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) {                    // D = 0: u is unchanged
+			st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
+			if (B.push_u) {
+#pragma unroll 1
+				for (int k = 0; k < A.X.npu; ++k)
+					if (c >= A.X.pu[k].lo && c < A.X.pu[k].hi && A.X.pu[k].dst) st2(A.X.pu[k].dst + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
+			}
+		}
 	}
 	// ---- residual of row rho = t-D-2 from stage D.  It lags the stages by one more row so that all its inputs (rows
 	// rho-1 .. rho+1 of stage D and the neighbours of row rho, fetched during the previous step) predate this step:
@@ -372,7 +408,13 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 					sum = add(sum, mul(A.R3.w[7], S.rw[RP][1]));
 					sum = add(sum, mul(A.R3.w[8], S.rw[RP][2]));
 				}
-				A.bc[(size_t)I * A.C.pitch + J] = (J < A.C.nj) ? sum : 0.0;
+				const double bcv = (J < A.C.nj) ? sum : 0.0;
+				A.bc[(size_t)I * A.C.pitch + J] = bcv;
+				if (B.push_b) {
+#pragma unroll 1
+					for (int k = 0; k < A.X.npb; ++k)
+						if (I >= A.X.pb[k].lo && I < A.X.pb[k].hi && A.X.pb[k].dst) A.X.pb[k].dst[(size_t)I * A.C.pitch + J] = bcv;
+				}
 			}
 		}
 		S.rw[(K - D - 2) & 3][0] = res.x; S.rw[(K - D - 2) & 3][1] = res.y;
@@ -440,6 +482,19 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 	}
 }
 
+// thread 0 of a block: spin until every listed flag has reached my version of its channel (bounded; see mgb_halo.cuh)
+__device__ __forceinline__ void jf_wait_list(const FusedComm &X, int which, int n)
+{
+	if (*(volatile int *)X.status != 0) return;                // a wait already timed out: do not spin again, the host aborts
+	const long long t0 = clock64();
+	for (int w = 0; w < n; ++w) {
+		const unsigned long long v = *(volatile const unsigned long long *)X.w_ver[which][w];
+		while (ld_acquire_sys(X.w_flag[which][w]) < v) {
+			if (clock64() - t0 > X.spin_limit) { atomicExch(X.status, 1); *(volatile int *)X.status_host = 1; return; }
+		}
+	}
+}
+
 template <int D, int PRE, int POST>
 __global__ void __launch_bounds__(FJ_THREADS, 4)
 k_jfused(FusedArgs A)
@@ -479,6 +534,19 @@ k_jfused(FusedArgs A)
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
 	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 3;
 	B.rbase = tb - 1;
+	B.push_u = false; B.push_b = false;
+	if (A.X.npu | A.X.npb | A.X.bc_remote | A.X.nw_top | A.X.nw_bot | A.X.nw_all) {
+		for (int k = 0; k < A.X.npu; ++k) B.push_u |= (D > 0 && B.y0 < A.X.pu[k].hi && B.y1 > A.X.pu[k].lo);
+		for (int k = 0; k < A.X.npb; ++k) B.push_b |= (POST == POST_RESTRICT && (B.y0 >> 1) < A.X.pb[k].hi && (B.y1 >> 1) > A.X.pb[k].lo);
+		// ghost rows above the strip are read by the blocks whose first step lies above row 0, ghost rows below it by those
+		// whose last step reaches row ni (the coarse rows of a prolongation follow the same fine rows)
+		if (threadIdx.x == 0) {
+			if (A.X.nw_all) jf_wait_list(A.X, 2, A.X.nw_all);
+			if (A.X.nw_top && tb - 1 < 0) jf_wait_list(A.X, 0, A.X.nw_top);
+			if (A.X.nw_bot && te + 1 >= F.ni) jf_wait_list(A.X, 1, A.X.nw_bot);
+		}
+		__syncthreads();
+	}
 	B.g_u = A.u_in + (B.c0 - FJ_HALO); B.g_b = A.b + (B.c0 - FJ_HALO);
 	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
 	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
@@ -491,4 +559,24 @@ k_jfused(FusedArgs A)
 		if (interior) jf_run<D, PRE, POST, false, 1>(A, B, sh, in_u, in_b, tb, te);
 		else          jf_run<D, PRE, POST, true, 1>(A, B, sh, in_u, in_b, tb, te);
 	} else            jf_run<D, PRE, POST, true, 0>(A, B, sh, in_u, in_b, tb, te);
+	// ---- signal: the last pushing block makes every pushed row visible system-wide, then raises the flags
+	if (A.X.nch) {
+		const bool takes = B.push_u || B.push_b || (A.X.bc_remote && POST == POST_RESTRICT);
+		if (takes) {
+			__syncthreads();                              // the block's stores are ordered before thread 0's fence (cumulativity)
+			if (threadIdx.x == 0) {
+				__threadfence_system();
+				const unsigned int t = atomicAdd(A.X.ticket, 1u);
+				if (t == (unsigned)A.X.npushblocks - 1u) {
+					*A.X.ticket = 0u;
+					__threadfence_system();
+					for (int c = 0; c < A.X.nch; ++c) {
+						const unsigned long long newv = *A.X.ver[c] + 1ull;
+						for (int k = 0; k < A.X.nsig[c]; ++k) st_relaxed_sys(A.X.sig[c][k], newv);
+						*A.X.ver[c] = newv;
+					}
+				}
+			}
+		}
+	}
 }

@@ -37,6 +37,7 @@ struct XferArgs {
 	unsigned long long *ver;                        // my version counter of the channel
 	unsigned int *ticket;                           // my block ticket counter of the channel (zero between launches)
 	int *status;                                    // status[0] != 0 after a timeout
+	int *status_host;                               // mapped host mirror of status[0] (the host tests it after every synchronisation)
 	int do_push, do_wait;
 	long long spin_limit;                           // clock64 ticks
 	unsigned long long parity_stride;               // doubles added to every dst when the new version is odd (all-reduce slots)
@@ -86,14 +87,24 @@ k_xfer(XferArgs a)
 	if (a.do_wait && threadIdx.x == 0) {
 		const unsigned long long v = *(volatile unsigned long long *)a.ver;
 		const long long t0 = clock64();
-		for (int w = 0; w < a.nwait; ++w) {
+		// after one timeout the ranks are out of step for good: later exchanges do not spin again (the host sees the
+		// status word after its next synchronisation and aborts the solve)
+		bool dead = *(volatile int *)a.status != 0;
+		for (int w = 0; w < a.nwait && !dead; ++w) {
 			while (ld_acquire_sys(a.wait_flag[w]) < v) {
-				if (clock64() - t0 > a.spin_limit) { atomicExch(a.status, 1); break; }
+				if (clock64() - t0 > a.spin_limit) {
+					atomicExch(a.status, 1);
+					if (a.status_host) *(volatile int *)a.status_host = 1;
+					dead = true; break;
+				}
 			}
 		}
 		__threadfence_system();
 	}
 }
+
+// keeps a channel's version counter in step on a rank that takes no part in a transfer done inside a compute kernel
+__global__ void k_bump(unsigned long long *ver) { *ver = *ver + 1ull; }
 
 // out[out_slot + k] = f(sum over ranks of slot[r][k]) in rank order (identical on every rank): the all-reduce tail.
 // slots: two parity sets of MGB_MAX_RANKS x 4 doubles (the set of the version just completed is read, so a fast

@@ -14,8 +14,8 @@
 #include <string.h>
 
 typedef struct { char *key; char *val; } PbOpt;
-static PbOpt *g_opt = NULL;
-static int g_n = 0, g_cap = 0;
+static __thread PbOpt *g_opt = NULL;   /* the options database is per thread (one session per thread) */
+static __thread int g_n = 0, g_cap = 0;
 
 static char *dupstr(const char *s) { size_t n = strlen(s) + 1; char *d = malloc(n); memcpy(d, s, n); return d; }
 

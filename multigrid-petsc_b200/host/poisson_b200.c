@@ -13,7 +13,7 @@
 #include <string.h>
 #include <unistd.h>
 
-extern jmp_buf *pb200_trap;
+extern __thread jmp_buf *pb200_trap;
 long long mgb_launch_count(const struct mgb_engine *e);
 double mgb_last_solve_ms(const struct mgb_engine *e);
 

@@ -31,14 +31,14 @@
 static mgb_engine *ENGINE(Assembly *assem) { return (mgb_engine *)(void *)assem->A2; }
 static void set_engine(Assembly *assem, mgb_engine *e) { assem->A2 = (Mat *)(void *)e; }
 
-static char g_msg[600];
+static __thread char g_msg[600];      /* per thread: two sessions on two threads keep their own message and trap */
 const char *pb200_last_error(void) { return g_msg; }
 
 /* Error convention of the reference: its API returns void and prints (ERROR_MSG, src/solver.c:3-6).  Here an
  * error on the accelerated path is fatal: print and exit(1) -- or, when the pipeline runs as a library call
  * (pb200_run), unwind to it through pb200_trap so that the caller gets a status and the message. */
 #include <setjmp.h>
-jmp_buf *pb200_trap = NULL;
+__thread jmp_buf *pb200_trap = NULL;
 
 static void bail(void)
 {

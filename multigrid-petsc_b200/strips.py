@@ -90,7 +90,7 @@ def _sum_over_ranks(x):
     return float(t.item())
 
 
-def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
+def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn, bench):
     """bench.py at N > 1: the same 8193^2 V(3,3) workload split into N row strips (strong scaling)."""
     import torch
     import torch.distributed as dist
@@ -123,8 +123,15 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
         k_busy += 1
     clocks = clk.stop() if rank == 0 else None
     value = steps / (ms * 1e-3)
-    # dominant kernel on this rank's strip: the fused down leg incl. its ghost-row / coarse-rhs exchange (collective)
+    # bit pattern checksum of the iterate after `steps` cycles from u = 0: must equal the 1-GPU one (bench.py prints it at N = 1)
     r0, r1 = e.local_rows(0)
+    parts = [None] * world
+    dist.all_gather_object(parts, bench.bits_fingerprint(e.get_vec(_pkg.VEC_U, 0)[r0:r1]))
+    fp_sum = sum(p[0] for p in parts) & 0xFFFFFFFFFFFFFFFF
+    fp_xor = 0
+    for p_ in parts:
+        fp_xor ^= p_[1]
+    # dominant kernel on this rank's strip: the fused down leg incl. its ghost-row / coarse-rhs exchange (collective)
     dist.barrier()
     torch.cuda.synchronize()
     t_j = _max_over_ranks(e.time_op("fused_down", 0, 20))
@@ -146,6 +153,16 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
     bp = [hosts[k % 2][0].data_ptr() for k in range(nsolve)]
     up = [hosts[k % 2][1].data_ptr() for k in range(nsolve)]
     s.solve_rhs_many(bp[:2], up[:2])
+    # (a) one Solve() at a time
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cycles1 = 0
+    for k in range(1 if a.profile else 3):
+        cycles1 += s.solve_rhs(hosts[k % 2][0].data_ptr(), hosts[k % 2][1].data_ptr())["num_iter"]
+    torch.cuda.synchronize()
+    t_single = _max_over_ranks(time.perf_counter() - t0)
+    # (b) the pipelined stream
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -155,11 +172,19 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
     cycles = sum(its)
     bytes_per_solve = 8.0 * n * n
     s.close()
+    # the same fingerprint on ONE GPU (rank 0, same process, after the strips are gone): proves strips == one strip bit for bit
+    fp1 = None
+    if rank == 0 and not a.profile:
+        s1 = _pkg.Session(options_fn(npts, levels, 1000, "-mgb_csr 0"))
+        s1.engine.solve_vcycle(sm, 3, 3, max_iter=steps, rtol=0.0)
+        fp1 = bench.bits_fingerprint(s1.engine.get_vec(_pkg.VEC_U, 0))
+        s1.close()
     if rank == 0:
-        line = {"metric": "V-cycles/sec (fp64, 8193^2 grid)", "value": value, "unit": "V-cycles/s", "n_gpus": world,
+        rec = bench.load_record(f"vcycle_{npts}")
+        line = {"metric": bench.METRIC, "value": value, "unit": "V-cycles/s", "n_gpus": world,
                 "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"2D Poisson {npts}^2 fp64, {levels}-level V(3,3), Richardson+Jacobi 0.8 (BASELINE configs[3])",
+                "config": {"workload": bench.WORKLOAD,
                            "unknowns": n * n, "l2": "inputs larger than L2 on every strip at N<=4; per-strip fine vector "
                            f"{8.0 * n * n / world / 1e6:.0f} MB", "parallelism": f"{world} row strips, P2P ghost rows over NVLink, "
                            "levels with <= 511 rows agglomerated on rank 0"},
@@ -169,10 +194,19 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn):
                              "traffic": None, "vcycle_gbs_unfused_count": 264.0 * n * n * value / 1e9},
                 "e2e": {"value": cycles / t_e2e, "unit": "V-cycles/s", "h2d_bytes_per_step": bytes_per_solve * nsolve / cycles,
                         "d2h_bytes_per_step": bytes_per_solve * nsolve / cycles, "solves": nsolve, "cycles_per_solve": cycles / nsolve,
+                        "single_solve_value": cycles1 / t_single,
                         "note": "a stream of right-hand sides (pb200_solve_rhs_many): per solve every rank uploads its rows of the rhs "
                                 "(pinned) + V-cycles to 1e-7 + reads its rows of u, copies overlapping the neighbouring solves; bytes are "
                                 "totals over the ranks, per V-cycle"},
-                "gpu_launches": int(launches), "final_relative_residual": float(rn[-1])}
+                "gpu_launches": int(launches), "final_relative_residual": float(rn[-1]),
+                "fingerprint": {"cycles": steps, "u_sum64": f"{fp_sum:#018x}", "u_xor64": f"{fp_xor:#018x}",
+                                "one_gpu_u_sum64": None if fp1 is None else f"{fp1[0]:#018x}",
+                                "one_gpu_u_xor64": None if fp1 is None else f"{fp1[1]:#018x}",
+                                "equals_one_gpu": None if fp1 is None else bool(fp1 == (fp_sum, fp_xor)),
+                                "note": "sum and xor of the 64-bit patterns of the fine-level iterate after `steps` cycles from u = 0, "
+                                        "combined over the strips; one_gpu_* = the same solve on rank 0's GPU alone in this run"}}
+        if rec:
+            line["parity"] = bench.parity_block(rn, rec)
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

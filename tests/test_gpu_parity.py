@@ -42,7 +42,7 @@ def _hex(v):
 
 # ------------------------------------------------------------------ assembled operators: bit-exact
 @pytest.mark.parametrize("npts,levels,mesh", [(5, 1, 0), (9, 2, 0), (17, 2, 0), (33, 4, 0), (101, 3, 0), (129, 4, 0),
-                                              (129, 7, 0), (65, 4, 1), (65, 4, 2), (257, 5, 0)])
+                                              (129, 7, 0), (65, 4, 1), (65, 4, 2), (257, 5, 0), (1025, 7, 0)])
 def test_csr_bit_exact(npts, levels, mesh):
     opts = base(npts, levels, mesh=mesh) + " " + JAC
     o = Oracle(opts)
@@ -293,6 +293,23 @@ def test_strips_emulated_cycle0_bit_exact(name, ranks, aggl):
     assert np.allclose(r["rnorm"], want, rtol=RTOL, atol=RNORM_ATOL)
     assert hashlib.sha256(np.ascontiguousarray(r["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]
     assert np.allclose(r["error"], _hex(g["error_hex"]), rtol=RTOL, atol=0.0)
+
+
+@pytest.mark.parametrize("name,ranks,aggl", [("n129_l7_jacobi", 2, 31), ("n129_l7_jacobi", 4, 15), ("n1025_l10_jacobi", 4, 0),
+                                             ("n129_l7_cg_mg", 2, 31)])
+def test_strips_emulated_separate_exchange_launches(name, ranks, aggl, monkeypatch):
+    """The fused legs normally push / wait for their ghost rows, the gathered right-hand side and the broadcast correction
+    themselves (FusedComm, csrc/mgb_fused.cuh); MGB_INKERNEL_HALO=0 selects the older protocol with one k_xfer launch per
+    exchange (csrc/mgb_halo.cuh).  Both must give the single-strip bits."""
+    monkeypatch.setenv("MGB_INKERNEL_HALO", "0")
+    g = GOLD[name]
+    r = mgb.run_poisson(g["options"] + f" -mgb_ranks {ranks} -mgb_emulate 1" + (f" -mgb_agglomerate {aggl}" if aggl else ""))
+    assert r["num_iter"] == g["num_iter"]
+    want = _hex(g["rnorm_hex"])
+    ok = ~np.isnan(want)
+    assert np.allclose(r["rnorm"][ok], want[ok], rtol=RTOL, atol=RNORM_ATOL)
+    if "-cycle 8" not in g["options"]:
+        assert hashlib.sha256(np.ascontiguousarray(r["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]
 
 
 @pytest.mark.parametrize("ranks", [2, 4])

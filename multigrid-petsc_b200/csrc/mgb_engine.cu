@@ -975,17 +975,40 @@ static int k_residual(mgb_engine *e, int l, int xv, int bv, int rv)
 	}
 	return MGB_OK;
 }
-// final stage of a reduction: local partials -> scal[slot] (single rank) or -> all-reduce over the ranks
+// final stage of a reduction in one launch (k_reduce_tail): local partials -> scal[slot] (+ its mapped host mirror), over all
+// ranks of a distributed level
 static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, int slot, int take_sqrt)
 {
 	const bool global = e->P > 1 && e->geo[l].dist;
+	const int chan = CH_REDUCE;
+	std::vector<TailArgs> args;
 	size_t i = 0;
 	for (auto &s : e->strips) {
 		if (!computes(s, l)) continue;
-		k_reduce2<<<1, 1024, 0, s.stream>>>(s.partial, nblocks[i++], s.scal, global ? SC_LOCAL : slot, global ? 0 : take_sqrt);
+		TailArgs a; memset(&a, 0, sizeof a);
+		a.partial = s.partial; a.n = nblocks[i++]; a.scal = s.scal; a.slot = slot; a.take_sqrt = take_sqrt; a.host = s.scal_host_dev;
+		a.nranks = global ? e->P : 1; a.do_push = 1; a.do_wait = 1;
+		if (global) {
+			const int r = s.rank;
+			for (int q = 0; q < e->P; ++q) {
+				a.slot_dst[q] = slots_of(e, q) + (size_t)r * RED_VALS;
+				a.peer_flag[q] = flags_of(e, q) + (size_t)chan * MGB_MAX_RANKS + r;
+				a.wait_flag[q] = flags_of(e, r) + (size_t)chan * MGB_MAX_RANKS + q;
+			}
+			a.my_slots = slots_of(e, r); a.ver = ver_of(e, s) + chan; a.parity_stride = (unsigned long long)MGB_MAX_RANKS * RED_VALS;
+			a.status = status_of(e, s); a.status_host = s.status_host_dev; a.spin_limit = e->spin_limit;
+			if (e->strips.size() > 1) a.do_wait = 0;               // emulation: every strip pushes first ...
+		}
+		k_reduce_tail<<<1, 1024, 0, s.stream>>>(a);
 		LAUNCHED(e); KCHECK();
+		args.push_back(a);
 	}
-	if (global) TRY(allreduce(e, 1, slot, take_sqrt));
+	if (global && e->strips.size() > 1)
+		for (size_t k = 0; k < args.size(); ++k) {                 // ... then every strip waits and sums
+			TailArgs a = args[k]; a.do_push = 0; a.do_wait = 1;
+			k_reduce_tail<<<1, 32, 0, e->strips[k].stream>>>(a);
+			LAUNCHED(e); KCHECK();
+		}
 	return MGB_OK;
 }
 // scal[slot] = || b - A x ||_2
@@ -1728,10 +1751,7 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0, true));  // :1540-1546
 			}
 		}
-		TRY(flush_all(e));
-		Strip &s0 = e->strips[0];
-		k_publish<<<1, 32, 0, s0.stream>>>(s0.scal_host_dev, s0.scal, 0, 1);
-		LAUNCHED(e); KCHECK();
+		TRY(flush_all(e));                                     // scal[0] is already in the mapped host mirror (k_reduce_tail)
 		return MGB_OK;
 	}
 	TRY(smooth(e, 0, s, p->v0, first, MGB_VEC_B, MGB_VEC_U, MGB_VEC_W));                          // :1531-1532
@@ -1745,9 +1765,6 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 	}
 	TRY(k_resnorm(e, 0, MGB_VEC_U, MGB_VEC_B, 0));                                                // :1545-1546
 	TRY(flush_all(e));
-	Strip &s0 = e->strips[0];
-	k_publish<<<1, 32, 0, s0.stream>>>(s0.scal_host_dev, s0.scal, 0, 1);
-	LAUNCHED(e); KCHECK();
 	return MGB_OK;
 }
 

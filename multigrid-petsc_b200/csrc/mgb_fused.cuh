@@ -189,7 +189,6 @@ struct JfBlock {
 	int tid, c0, j0, y0, y1;
 	ptrdiff_t P;
 	bool in0, in1, ld_ok, st_ok;
-	bool push_u, push_b;     // this block's rows intersect a push range of u_out / of the coarse right-hand side
 	bool tma;                // input rows arrive by TMA bulk copies (pitch >= FJ_COLS) instead of per-thread cp.async
 	int rbase;               // first row of the input rings: row i lives in slot (i - rbase) & (FJ_NR - 1)
 	unsigned long long *bar; // FJ_NR mbarriers, one per ring slot (TMA path)
@@ -343,14 +342,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	// ---- the finished row t-D
 	{
 		const int c = t - D;
-		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) {                    // D = 0: u is unchanged
-			st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
-			if (B.push_u) {
-#pragma unroll 1
-				for (int k = 0; k < A.X.npu; ++k)
-					if (c >= A.X.pu[k].lo && c < A.X.pu[k].hi && A.X.pu[k].dst) st2(A.X.pu[k].dst + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
-			}
-		}
+		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);   // D = 0: u is unchanged
 	}
 	// ---- residual of row rho = t-D-2 from stage D.  It lags the stages by one more row so that all its inputs (rows
 	// rho-1 .. rho+1 of stage D and the neighbours of row rho, fetched during the previous step) predate this step:
@@ -408,13 +400,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 					sum = add(sum, mul(A.R3.w[7], S.rw[RP][1]));
 					sum = add(sum, mul(A.R3.w[8], S.rw[RP][2]));
 				}
-				const double bcv = (J < A.C.nj) ? sum : 0.0;
-				A.bc[(size_t)I * A.C.pitch + J] = bcv;
-				if (B.push_b) {
-#pragma unroll 1
-					for (int k = 0; k < A.X.npb; ++k)
-						if (I >= A.X.pb[k].lo && I < A.X.pb[k].hi && A.X.pb[k].dst) A.X.pb[k].dst[(size_t)I * A.C.pitch + J] = bcv;
-				}
+				A.bc[(size_t)I * A.C.pitch + J] = (J < A.C.nj) ? sum : 0.0;
 			}
 		}
 		S.rw[(K - D - 2) & 3][0] = res.x; S.rw[(K - D - 2) & 3][1] = res.y;
@@ -534,10 +520,7 @@ k_jfused(FusedArgs A)
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
 	const int tb = (B.y0 - D - 1) & ~3, te = B.y1 + D + 3;
 	B.rbase = tb - 1;
-	B.push_u = false; B.push_b = false;
-	if (A.X.npu | A.X.npb | A.X.bc_remote | A.X.nw_top | A.X.nw_bot | A.X.nw_all) {
-		for (int k = 0; k < A.X.npu; ++k) B.push_u |= (D > 0 && B.y0 < A.X.pu[k].hi && B.y1 > A.X.pu[k].lo);
-		for (int k = 0; k < A.X.npb; ++k) B.push_b |= (POST == POST_RESTRICT && (B.y0 >> 1) < A.X.pb[k].hi && (B.y1 >> 1) > A.X.pb[k].lo);
+	if (A.X.nw_top | A.X.nw_bot | A.X.nw_all) {
 		// ghost rows above the strip are read by the blocks whose first step lies above row 0, ghost rows below it by those
 		// whose last step reaches row ni (the coarse rows of a prolongation follow the same fine rows)
 		if (threadIdx.x == 0) {
@@ -559,9 +542,34 @@ k_jfused(FusedArgs A)
 		if (interior) jf_run<D, PRE, POST, false, 1>(A, B, sh, in_u, in_b, tb, te);
 		else          jf_run<D, PRE, POST, true, 1>(A, B, sh, in_u, in_b, tb, te);
 	} else            jf_run<D, PRE, POST, true, 0>(A, B, sh, in_u, in_b, tb, te);
-	// ---- signal: the last pushing block makes every pushed row visible system-wide, then raises the flags
+	// ---- push: the rows of this block that lie in a push range travel to the peers AFTER the row loop (nothing of this is
+	// in the hot loop): every thread re-reads exactly the elements it stored itself, so no fence is needed in between
 	if (A.X.nch) {
-		const bool takes = B.push_u || B.push_b || (A.X.bc_remote && POST == POST_RESTRICT);
+		// (computed here, not carried through the row loop: the kernel runs at the 128-register cap)
+		bool push_u = false, push_b = false;
+		for (int k = 0; k < A.X.npu; ++k) push_u |= (D > 0 && B.y0 < A.X.pu[k].hi && B.y1 > A.X.pu[k].lo);
+		for (int k = 0; k < A.X.npb; ++k) push_b |= (POST == POST_RESTRICT && (B.y0 >> 1) < A.X.pb[k].hi && (B.y1 >> 1) > A.X.pb[k].lo);
+		const bool takes = push_u || push_b || (A.X.bc_remote && POST == POST_RESTRICT);
+		if (push_u && B.st_ok) {
+			for (int k = 0; k < A.X.npu; ++k) {
+				double *dst = A.X.pu[k].dst;
+				if (!dst) continue;
+				const int c0 = max(B.y0, A.X.pu[k].lo), c1 = min(B.y1, A.X.pu[k].hi);
+				for (int c = c0; c < c1; ++c) st2(dst + (ptrdiff_t)c * B.P + B.j0, ld2(A.u_out + (ptrdiff_t)c * B.P + B.j0));
+			}
+		}
+		if (push_b && B.st_ok) {
+			const int J = B.j0 >> 1;
+			if (J < A.C.pitch) {
+				for (int k = 0; k < A.X.npb; ++k) {
+					double *dst = A.X.pb[k].dst;
+					if (!dst) continue;
+					const int I0 = max(B.y0 >> 1, A.X.pb[k].lo), I1 = min(min(B.y1 >> 1, A.C.ni), A.X.pb[k].hi);
+					for (int I = I0; I < I1; ++I) dst[(size_t)I * A.C.pitch + J] = A.bc[(size_t)I * A.C.pitch + J];
+				}
+			}
+		}
+		// ---- signal: the last pushing block makes every pushed row visible system-wide, then raises the flags
 		if (takes) {
 			__syncthreads();                              // the block's stores are ordered before thread 0's fence (cumulativity)
 			if (threadIdx.x == 0) {

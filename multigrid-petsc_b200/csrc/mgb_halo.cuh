@@ -103,6 +103,75 @@ k_xfer(XferArgs a)
 	}
 }
 
+// The tail of every norm / dot product in ONE launch of one block: sum of the per-block partials in a fixed order, then
+//   single strip:  out[slot] = f(sum), mirrored into mapped host memory (no separate publish launch);
+//   row strips:    the local sum goes into slot [my rank] of every rank (parity sets as in k_reduce_ranks), the flags are
+//                  raised, the peers' flags are awaited and the slots are summed in rank order -- identical values and
+//                  identical stopping decisions on every rank (replaces k_reduce2 + k_xfer + k_reduce_ranks + k_publish).
+// do_push / do_wait split the two halves for strips emulated on one GPU (all pushes first, then the waits).
+struct TailArgs {
+	const double *partial; int n;
+	double *scal; int slot, take_sqrt;
+	double *host;                                   // mapped host mirror of scal[] (or null)
+	int nranks;
+	double *slot_dst[MGB_MAX_RANKS];                // slot [my rank] in every rank's slot array (parity offset added here)
+	unsigned long long *peer_flag[MGB_MAX_RANKS];
+	const unsigned long long *wait_flag[MGB_MAX_RANKS];
+	const double *my_slots;
+	unsigned long long *ver;
+	unsigned long long parity_stride;
+	int *status, *status_host;
+	long long spin_limit;
+	int do_push, do_wait;
+};
+
+__global__ void __launch_bounds__(1024)
+k_reduce_tail(TailArgs a)
+{
+	double s = 0.0;
+	if (a.do_push) {
+		double acc = 0.0;
+		for (int k = threadIdx.x; k < a.n; k += 1024) acc += a.partial[k];
+		s = block_sum<1024>(acc);
+	}
+	if (threadIdx.x != 0) return;
+	if (a.nranks <= 1) {
+		const double v = a.take_sqrt ? sqrt(s) : s;
+		a.scal[a.slot] = v;
+		if (a.host) { a.host[a.slot] = v; __threadfence_system(); }
+		return;
+	}
+	if (a.do_push) {
+		const unsigned long long newv = *a.ver + 1ull;
+		const unsigned long long par = (newv & 1ull) ? a.parity_stride : 0ull;
+		for (int q = 0; q < a.nranks; ++q) a.slot_dst[q][par] = s;
+		__threadfence_system();
+		for (int q = 0; q < a.nranks; ++q) st_relaxed_sys(a.peer_flag[q], newv);
+		*a.ver = newv;
+	}
+	if (a.do_wait) {
+		const unsigned long long v = *(volatile unsigned long long *)a.ver;
+		const long long t0 = clock64();
+		bool dead = *(volatile int *)a.status != 0;
+		for (int q = 0; q < a.nranks && !dead; ++q) {
+			while (ld_acquire_sys(a.wait_flag[q]) < v) {
+				if (clock64() - t0 > a.spin_limit) {
+					atomicExch(a.status, 1);
+					if (a.status_host) *(volatile int *)a.status_host = 1;
+					dead = true; break;
+				}
+			}
+		}
+		__threadfence_system();
+		const double *sl = a.my_slots + ((v & 1ull) ? a.parity_stride : 0ull);
+		double t = 0.0;
+		for (int r = 0; r < a.nranks; ++r) t += *(volatile const double *)(sl + r * 4);
+		const double o = a.take_sqrt ? sqrt(t) : t;
+		a.scal[a.slot] = o;
+		if (a.host) { a.host[a.slot] = o; __threadfence_system(); }
+	}
+}
+
 // keeps a channel's version counter in step on a rank that takes no part in a transfer done inside a compute kernel
 __global__ void k_bump(unsigned long long *ver) { *ver = *ver + 1ull; }
 

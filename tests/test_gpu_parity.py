@@ -295,7 +295,7 @@ def test_strips_emulated_cycle0_bit_exact(name, ranks, aggl):
     assert np.allclose(r["error"], _hex(g["error_hex"]), rtol=RTOL, atol=0.0)
 
 
-@pytest.mark.parametrize("name,ranks,aggl", [("n129_l7_jacobi", 2, 31), ("n129_l7_jacobi", 4, 15), ("n1025_l10_jacobi", 4, 0),
+@pytest.mark.parametrize("name,ranks,aggl", [("n129_l7_jacobi", 2, 31), ("n129_l7_jacobi", 4, 31), ("n1025_l10_jacobi", 4, 0),
                                              ("n129_l7_cg_mg", 2, 31)])
 def test_strips_emulated_separate_exchange_launches(name, ranks, aggl, monkeypatch):
     """The fused legs normally push / wait for their ghost rows, the gathered right-hand side and the broadcast correction

@@ -196,6 +196,7 @@ typedef struct {
 	int    coarse;           /* MGB_COARSE_*                                                      */
 	mgb_smoother coarse_smoother; int coarse_its;   /* -mg_coarse_*                               */
 	int    no_fuse, no_bottom; /* as in mgb_vcycle_params                                          */
+	int    no_graph;         /* 1: launch the kernels of a CG iteration one by one (default 0: one CUDA graph per iteration) */
 } mgb_pcmg_params;
 /* reason: >0 converged (2 = rtol, 3 = atol, 4 = its), <0 diverged (PETSc KSPConvergedReason values) */
 int  mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *rnorm, int *num_iter, int *reason, double *seconds);

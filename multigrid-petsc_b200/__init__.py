@@ -75,7 +75,8 @@ class VcycleParams(C.Structure):
 class PcmgParams(C.Structure):
     _fields_ = [("outer", C.c_int), ("rtol", C.c_double), ("abstol", C.c_double), ("dtol", C.c_double),
                 ("max_iter", C.c_int), ("level_smoother", Smoother), ("level_its", C.c_int), ("coarse", C.c_int),
-                ("coarse_smoother", Smoother), ("coarse_its", C.c_int), ("no_fuse", C.c_int), ("no_bottom", C.c_int)]
+                ("coarse_smoother", Smoother), ("coarse_its", C.c_int), ("no_fuse", C.c_int), ("no_bottom", C.c_int),
+                ("no_graph", C.c_int)]
 
 
 class RunResult(C.Structure):
@@ -320,9 +321,10 @@ class Engine:
         return it.value, rn[: it.value + 1].copy(), sec.value
 
     def solve_pcmg(self, outer, level_smoother, level_its, coarse=COARSE_LU, coarse_smoother=None, coarse_its=1,
-                   rtol=1e-7, abstol=1e-50, dtol=1e4, max_iter=100, fuse=True, bottom=True):
+                   rtol=1e-7, abstol=1e-50, dtol=1e4, max_iter=100, fuse=True, bottom=True, graph=True):
         cs = coarse_smoother if coarse_smoother is not None else jacobi(1.0)
-        p = PcmgParams(outer, rtol, abstol, dtol, max_iter, level_smoother, level_its, coarse, cs, coarse_its, int(not fuse), int(not bottom))
+        p = PcmgParams(outer, rtol, abstol, dtol, max_iter, level_smoother, level_its, coarse, cs, coarse_its, int(not fuse), int(not bottom),
+                       int(not graph))
         rn = np.zeros(max_iter + 1)
         it, reason, sec = C.c_int(), C.c_int(), C.c_double()
         self._ck(self.L.mgb_solve_pcmg(self.h, C.byref(p), _pd(rn), C.byref(it), C.byref(reason), C.byref(sec)))

@@ -141,8 +141,9 @@ __global__ void k_publish(double *__restrict__ host_mapped, const double *__rest
 // x += a p ; r -= a w ; partial[block] = sum r^2.  40 B per unknown instead of 24 + 24 + 8.
 __global__ void __launch_bounds__(MGB_RED_THREADS)
 k_cg_update(double *__restrict__ x, const double *__restrict__ p, double *__restrict__ r, const double *__restrict__ w,
-            size_t n2, double a, double *__restrict__ partial)
+            size_t n2, double a, double *__restrict__ partial, const double *__restrict__ a_dev)
 {
+	if (a_dev) a = a_dev[0];                      // alpha = beta / p'w as left by the reduction tail (TAIL_DPI)
 	double acc = 0.0;
 	const double ma = -a;
 	const size_t stride = (size_t)gridDim.x * MGB_RED_THREADS;

@@ -977,7 +977,7 @@ static int k_residual(mgb_engine *e, int l, int xv, int bv, int rv)
 }
 // final stage of a reduction in one launch (k_reduce_tail): local partials -> scal[slot] (+ its mapped host mirror), over all
 // ranks of a distributed level
-static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, int slot, int take_sqrt)
+static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, int slot, int take_sqrt, int post_op = TAIL_NONE)
 {
 	const bool global = e->P > 1 && e->geo[l].dist;
 	const int chan = CH_REDUCE;
@@ -987,7 +987,7 @@ static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, in
 		if (!computes(s, l)) continue;
 		TailArgs a; memset(&a, 0, sizeof a);
 		a.partial = s.partial; a.n = nblocks[i++]; a.scal = s.scal; a.slot = slot; a.take_sqrt = take_sqrt; a.host = s.scal_host_dev;
-		a.nranks = global ? e->P : 1; a.do_push = 1; a.do_wait = 1;
+		a.nranks = global ? e->P : 1; a.do_push = 1; a.do_wait = 1; a.post_op = post_op;
 		if (global) {
 			const int r = s.rank;
 			for (int q = 0; q < e->P; ++q) {
@@ -1030,7 +1030,7 @@ static int k_resnorm(mgb_engine *e, int l, int xv, int bv, int slot)
 	return reduce_tail(e, l, nb, slot, 1);
 }
 // scal[slot] = sqrt?(sum x*y) (yv < 0: sum x*x)
-static int k_reduce(mgb_engine *e, int l, int xv, int yv, int slot, int take_sqrt)
+static int k_reduce(mgb_engine *e, int l, int xv, int yv, int slot, int take_sqrt, int post_op = TAIL_NONE)
 {
 	const LevelGeom &g = e->geo[l];
 	std::vector<int> nb;
@@ -1045,10 +1045,10 @@ static int k_reduce(mgb_engine *e, int l, int xv, int yv, int slot, int take_sqr
 		LAUNCHED(e); KCHECK();
 		nb.push_back(blocks);
 	}
-	return reduce_tail(e, l, nb, slot, take_sqrt);
+	return reduce_tail(e, l, nb, slot, take_sqrt, post_op);
 }
 template <int KIND>
-static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha)
+static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha, int alpha_slot = -1)
 {
 	const LevelGeom &g = e->geo[l];
 	for (auto &s : e->strips) {
@@ -1057,13 +1057,13 @@ static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha)
 		const size_t n2 = (size_t)S.ni * g.pitch / 2;
 		size_t want = (n2 + 255) / 256;
 		const int blocks = (int)(want < 1 ? 1 : (want > 148 * 32 ? 148 * 32 : want));
-		k_axpy<KIND><<<blocks, 256, 0, s.stream>>>(S.v[yv], S.v[xv], n2, alpha, nullptr, 0.0);
+		k_axpy<KIND><<<blocks, 256, 0, s.stream>>>(S.v[yv], S.v[xv], n2, alpha, alpha_slot >= 0 ? s.scal + alpha_slot : nullptr, 1.0);
 		LAUNCHED(e); KCHECK();
 	}
 	return MGB_OK;
 }
 // y = A x ; scal[slot] = x . y in one pass (the w = A p, p'w pair of CG)
-static int k_apply_dot(mgb_engine *e, int l, int xv, int yv, int slot)
+static int k_apply_dot(mgb_engine *e, int l, int xv, int yv, int slot, int post_op = TAIL_NONE)
 {
 	TRY(flush_levels(e, l, l));
 	const LevelGeom &g = e->geo[l];
@@ -1078,10 +1078,10 @@ static int k_apply_dot(mgb_engine *e, int l, int xv, int yv, int slot)
 		LAUNCHED(e); KCHECK();
 		nb.push_back((int)(gr.x * gr.y));
 	}
-	return reduce_tail(e, l, nb, slot, 0);
+	return reduce_tail(e, l, nb, slot, 0, post_op);
 }
 // x += a p ; r -= a w ; scal[slot] = ||r||_2 in one pass (the CG update, mgb_blas.cuh: k_cg_update)
-static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, double a, int slot)
+static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, double a, int slot, int a_slot = -1)
 {
 	const LevelGeom &g = e->geo[l];
 	std::vector<int> nb;
@@ -1091,7 +1091,7 @@ static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, doubl
 		const size_t n2 = (size_t)S.ni * g.pitch / 2;
 		size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
 		const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
-		k_cg_update<<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial);
+		k_cg_update<<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial, a_slot >= 0 ? s.scal + a_slot : nullptr);
 		LAUNCHED(e); KCHECK();
 		nb.push_back(blocks);
 	}
@@ -1100,10 +1100,11 @@ static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, doubl
 // scal[first .. first+count) of the first local strip -> its pinned mirror (every rank holds identical values)
 static int read_scalars(mgb_engine *e, int first, int count)
 {
+	// every reduction ends in k_reduce_tail, which mirrors its result into the mapped host copy of scal[]: only a stream
+	// synchronisation is needed here (no publish launch, no copy)
+	(void)first; (void)count;
 	TRY(flush_all(e));
 	Strip &s = e->strips[0];
-	k_publish<<<1, 32, 0, s.stream>>>(s.scal_host_dev, s.scal, first, count);
-	LAUNCHED(e); KCHECK();
 	CU(cudaStreamSynchronize(s.stream));
 	return quick_status(e);
 }
@@ -1307,7 +1308,7 @@ static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cud
 	JF(PRE_GIVEN, POST_NONE) JF(PRE_GIVEN, POST_RESTRICT) JF(PRE_GIVEN, POST_NORM)
 	JF(PRE_ZERO, POST_NONE) JF(PRE_ZERO, POST_RESTRICT) JF(PRE_ZERO, POST_NORM)
 	JF(PRE_PROLONG, POST_NONE) JF(PRE_PROLONG, POST_NORM)
-	JF(PRE_PROLONG_MULTADD, POST_NONE) JF(PRE_PROLONG_MULTADD, POST_NORM)
+	JF(PRE_PROLONG_MULTADD, POST_NONE) JF(PRE_PROLONG_MULTADD, POST_DOT)
 #undef JF
 	return fail(MGB_EINVAL, "fused kernel: combination pre %d / post %d not built", pre, post);
 }
@@ -1517,7 +1518,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 				if (need > tiles) tiles = need;
 			}
 			dim3 grid(tiles, cdiv(S.ni, a.rows));
-			if (post_k == POST_NORM) {
+			if (post_k == POST_NORM || post_k == POST_DOT) {
 				if ((size_t)grid.x * grid.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
 				a.partial = s.partial;
 				nb.push_back((int)(grid.x * grid.y));
@@ -1541,6 +1542,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			}
 		}
 		if (post_k == POST_NORM) TRY(reduce_tail(e, l, nb, norm_slot, 1));
+		if (post_k == POST_DOT) TRY(reduce_tail(e, l, nb, norm_slot, 0, TAIL_BETA));     // z'r of CG, with beta / ratio derived on the device
 		done += D;
 	}
 	return MGB_OK;
@@ -1787,17 +1789,48 @@ static void load_state(mgb_engine *e, const std::vector<PtrState> &st)
 		for (int l = 0; l < e->L; ++l)
 			for (int k = 0; k < MGB_NVEC; ++k) { e->strips[i].lev[l].v[k] = st[i].v[l][k]; e->strips[i].lev[l].phys[k] = st[i].phys[l][k]; }
 }
-// A captured cycle is valid for one set of parameters and one assignment of the ping-pong pointers: that is the key.
-static std::vector<char> graph_key(mgb_engine *e, const mgb_vcycle_params *p)
+// Replay `body` (kernel launches on the strips' stream, no synchronisation) as a CUDA graph.  A captured body is valid for one
+// set of parameters (`key`) and one assignment of the ping-pong pointers, which is appended to the key; the pointer state
+// after the body is a pure function of the state before it and is restored on replay.
+template <class F>
+static int run_graphed(mgb_engine *e, std::vector<char> key, F body)
 {
-	std::vector<char> k(sizeof *p);
-	memcpy(k.data(), p, sizeof *p);
+	Strip &s0 = e->strips[0];
 	for (auto &s : e->strips)
 		for (int l = 0; l < e->L; ++l) {
 			const char *b = (const char *)s.lev[l].v;
-			k.insert(k.end(), b, b + sizeof s.lev[l].v);
+			key.insert(key.end(), b, b + sizeof s.lev[l].v);
 		}
-	return k;
+	GraphEntry *g = nullptr;
+	for (auto &c : e->gcache) if (c.key == key) { g = &c; break; }
+	if (!g) {
+		cudaGraph_t graph = nullptr;
+		const long long l0 = e->launches;
+		std::vector<PtrState> before; save_state(e, before);
+		CU(cudaStreamBeginCapture(s0.stream, cudaStreamCaptureModeThreadLocal));
+		int r = body();
+		cudaError_t ce = cudaStreamEndCapture(s0.stream, &graph);     // always ends the capture, also after a failed body
+		if (r != MGB_OK || ce != cudaSuccess) {
+			if (graph) cudaGraphDestroy(graph);
+			load_state(e, before); e->launches = l0; e->pending.clear();
+			if (r != MGB_OK) return r;
+			return fail(MGB_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+		}
+		GraphEntry ne; ne.key = key; ne.exec = nullptr;
+		ce = cudaGraphInstantiate(&ne.exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (ce != cudaSuccess) { load_state(e, before); e->launches = l0; return fail(MGB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+		ne.launches = e->launches - l0;
+		e->launches = l0;
+		save_state(e, ne.after);
+		e->gcache.push_back(ne);
+		g = &e->gcache.back();
+	} else {
+		load_state(e, g->after);
+	}
+	CU(cudaGraphLaunch(g->exec, s0.stream));
+	e->launches += g->launches;
+	return MGB_OK;
 }
 
 // the cycle loop of MultigridVcycle on the right-hand side in B[0] (ref: src/solver.c:1512-1558); rnorm holds
@@ -1819,41 +1852,13 @@ static int vcycle_solve(mgb_engine *e, const mgb_vcycle_params *p, double *rnorm
 	// the timed region of the reference starts here, after rnorm[0] (t0 = MPI_Wtime() at src/solver.c:1526)
 	if (mark_loop_start) CU(cudaEventRecord(s0.ev0, s0.stream));
 	while (iter < p->max_iter && 100000000.0 * bnorm > rn && rn > p->rtol * bnorm) {              // :1530
-		if (!p->use_graph || iter == 0) {
+		if (!p->use_graph) {
 			TRY(vcycle_body(e, p, iter == 0));
 		} else {
-			const std::vector<char> key = graph_key(e, p);
-			GraphEntry *g = nullptr;
-			for (auto &c : e->gcache) if (c.key == key) { g = &c; break; }
-			if (!g) {
-				// capture: the pointer state after the cycle is a pure function of the state before it
-				cudaGraph_t graph;
-				const long long l0 = e->launches;
-				CU(cudaStreamBeginCapture(s0.stream, cudaStreamCaptureModeThreadLocal));
-				std::vector<PtrState> before; save_state(e, before);
-				graph = nullptr;
-				int r = vcycle_body(e, p, false);
-				cudaError_t ce = cudaStreamEndCapture(s0.stream, &graph);     // always ends the capture, also after a failed body
-				if (r != MGB_OK || ce != cudaSuccess) {
-					if (graph) cudaGraphDestroy(graph);
-					load_state(e, before); e->launches = l0; e->pending.clear();
-					if (r != MGB_OK) return r;
-					return fail(MGB_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-				}
-				GraphEntry ne; ne.key = key; ne.exec = nullptr;
-				ce = cudaGraphInstantiate(&ne.exec, graph, 0);
-				cudaGraphDestroy(graph);
-				if (ce != cudaSuccess) { load_state(e, before); e->launches = l0; return fail(MGB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
-				ne.launches = e->launches - l0;
-				e->launches = l0;
-				save_state(e, ne.after);
-				e->gcache.push_back(ne);
-				g = &e->gcache.back();
-			} else {
-				load_state(e, g->after);
-			}
-			CU(cudaGraphLaunch(g->exec, s0.stream));
-			e->launches += g->launches;
+			const bool first = iter == 0;                            // the first cycle starts from u = 0 (PRE_ZERO leg): its own graph
+			std::vector<char> key(sizeof *p + 1, first ? 'F' : 'V');
+			memcpy(key.data() + 1, p, sizeof *p);
+			TRY(run_graphed(e, key, [&]() { return vcycle_body(e, p, first); }));
 		}
 		CU(cudaStreamSynchronize(s0.stream));
 		TRY(quick_status(e));
@@ -1948,7 +1953,9 @@ extern "C" int mgb_solve_vcycle_many(mgb_engine *e, const mgb_vcycle_params *p, 
 
 // ------------------------------------------------------------------------------------------------ cycle 8
 // PCApply_MG (multiplicative V, one cycle, x = 0 on entry) on level l with right-hand side bv and iterate xv.
-static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, int xv)
+// dot_slot >= 0 (level 0 only): also leave scal[dot_slot] = xv . bv (the z'r of CG, with TAIL_BETA) when the last leg can
+// produce it in passing (*dot_done = true), else the caller computes it
+static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, int xv, int dot_slot = -1, bool *dot_done = nullptr)
 {
 	const int Lc = e->L;
 	// the gathered right-hand side of the first agglomerated level: the fused legs wait for it themselves, every other consumer
@@ -1977,7 +1984,9 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_ZERO, POST_RESTRICT, bv, xv, MGB_VEC_W, 0));
 		TRY(pcmg_cycle(e, p, l + 1, MGB_VEC_B, MGB_VEC_U));
 		if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(need_bcast(e, l + 1));
-		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_PROLONG_MULTADD, POST_NONE, bv, xv, MGB_VEC_W, 0, true));
+		const bool dot = l == 0 && dot_slot >= 0 && dot_done;
+		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_PROLONG_MULTADD, dot ? POST_DOT : POST_NONE, bv, xv, MGB_VEC_W, dot ? dot_slot : 0, true));
+		if (dot) *dot_done = true;
 		return MGB_OK;
 	}
 	TRY(smooth(e, l, &p->level_smoother, p->level_its, true, bv, xv, MGB_VEC_W));     // pre-smooth from x = 0
@@ -2038,35 +2047,50 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 	TRY(vec_zero(e, X, 0));                                  // KSPSolve: zero initial guess
 	TRY(k_vecop<2>(e, 0, R, B, 0.0));                        // r = b
 	if (p->outer == MGB_KSP_CG) {
-		// KSPSolve_CG, KSP_NORM_UNPRECONDITIONED (ref: src/solver.c:1922)
+		// KSPSolve_CG, KSP_NORM_UNPRECONDITIONED (ref: src/solver.c:1922).  One iteration is ONE graph launch and ONE host
+		// read-back (||r||): beta = z'r, b = beta / betaold, dpi = p'w and a = beta / dpi are derived on the device where the
+		// dot products finish (k_reduce_tail, TAIL_*), the vector kernels read them from HBM.  The host sees all of them in
+		// the mapped mirror after the synchronisation and applies PETSc's tests in PETSc's order; the only difference to a
+		// host-driven loop is that on an indefinite-operator / indefinite-preconditioner exit x and r have already taken the
+		// update of that iteration.
 		double beta = 0.0, betaold = 1.0, dpi = 0.0, dpiold;
 		TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
 		logr(dp);
 		reason = ksp_converged(p, 0, dp, &rnorm0, &ttol);
 		if (!reason) {
-			TRY(precond());                                                                        // z = B r
-			TRY(k_reduce(e, 0, Z, R, 0, 0)); TRY(read_scalars(e, 0, 1)); beta = hs[0];             // beta = z'r
+			TRY(vec_zero(e, Pv, 0));                                                               // p = 0: the first p = z + 0 p
+			for (auto &s : e->strips) { k_set_scalar<<<1, 1, 0, s.stream>>>(s.scal + SC_BETA, INFINITY); LAUNCHED(e); KCHECK(); }
+			auto iteration = [&]() -> int {
+				bool dot_done = false;
+				TRY(halo(e, 0, R, HALO_DEPTH));
+				TRY(pcmg_cycle(e, p, 0, R, Z, 2, &dot_done));                                      // z = B r  [; beta = z'r]
+				if (!dot_done) TRY(k_reduce(e, 0, Z, R, 2, 0, TAIL_BETA));                         // beta = z'r ; b = beta / betaold
+				TRY(k_vecop<1>(e, 0, Pv, Z, 0.0, SC_RATIO));                                       // p = z + b p
+				TRY(halo(e, 0, Pv, 2));
+				TRY(k_apply_dot(e, 0, Pv, Q, 3, TAIL_DPI));                                        // w = A p ; dpi = p'w ; a = beta / dpi
+				TRY(k_cg_step(e, 0, X, Pv, R, Q, 0.0, 0, SC_ALPHA));                               // x += a p ; r -= a w ; ||r||
+				return flush_all(e);
+			};
+			if (e->gcache.size() > 16) drop_graphs(e);
 			int i = 0;
 			do {
 				its = i + 1;
+				if (p->no_graph) TRY(iteration());
+				else {
+					std::vector<char> key(sizeof *p + 1, 'C');
+					memcpy(key.data() + 1, p, sizeof *p);
+					TRY(run_graphed(e, key, iteration));
+				}
+				CU(cudaStreamSynchronize(s0.stream));
+				TRY(quick_status(e));
+				betaold = beta; dpiold = dpi;
+				beta = hs[SC_BETA]; dpi = hs[SC_DPI]; dp = hs[0];
 				if (beta == 0.0) { reason = 3; break; }
 				else if (i > 0 && beta * betaold < 0.0) { reason = -8; break; }                    // KSP_DIVERGED_INDEFINITE_PC
-				if (i == 0) { TRY(k_vecop<2>(e, 0, Pv, Z, 0.0)); }                                 // p = z
-				else { TRY(k_vecop<1>(e, 0, Pv, Z, beta / betaold)); }                             // p = z + b p
-				dpiold = dpi;
-				TRY(halo(e, 0, Pv, 2));
-				TRY(k_apply_dot(e, 0, Pv, Q, 0));                                                  // w = A p ; dpi = p'w
-				TRY(read_scalars(e, 0, 1)); dpi = hs[0];
-				betaold = beta;
 				if (dpi == 0.0 || (i > 0 && dpi * dpiold <= 0.0)) { reason = -10; break; }         // KSP_DIVERGED_INDEFINITE_MAT
-				const double a = beta / dpi;
-				TRY(k_cg_step(e, 0, X, Pv, R, Q, a, 0));                                           // x = x + a p ; r = r - a w ; ||r||
-				TRY(read_scalars(e, 0, 1)); dp = hs[0];
 				logr(dp);
 				reason = ksp_converged(p, i + 1, dp, &rnorm0, &ttol);
 				if (reason) break;
-				TRY(precond());
-				TRY(k_reduce(e, 0, Z, R, 0, 0)); TRY(read_scalars(e, 0, 1)); beta = hs[0];
 				i++;
 			} while (i < p->max_iter);
 			if (i >= p->max_iter && !reason) reason = -3;                                          // KSP_DIVERGED_ITS

@@ -80,7 +80,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned smem, const void *gmem, unsign
 }
 
 enum { PRE_GIVEN = 0, PRE_ZERO = 1, PRE_PROLONG = 2, PRE_PROLONG_MULTADD = 3 };
-enum { POST_NONE = 0, POST_RESTRICT = 1, POST_NORM = 2 };
+enum { POST_NONE = 0, POST_RESTRICT = 1, POST_NORM = 2, POST_DOT = 3 };   // POST_DOT: sum u_out . b over the finished rows (the z'r of CG)
 
 // Strip-to-strip traffic done BY the fused kernel (no separate exchange launch; protocol notes in mgb_halo.cuh):
 //   push   finished rows of u_out / of the coarse right-hand side that lie in a push range are also stored into a peer's
@@ -342,13 +342,19 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	// ---- the finished row t-D
 	{
 		const int c = t - D;
-		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);   // D = 0: u is unchanged
+		if (D > 0 && B.st_ok && c >= B.y0 && c < B.y1) {                    // D = 0: u is unchanged
+			st2(A.u_out + (ptrdiff_t)c * B.P + B.j0, S.win[D][(K - D) & 3]);
+			if (POST == POST_DOT) {                                              // b of row t-D is still in the ring (D <= 3)
+				const double2 o = S.win[D][(K - D) & 3], bb = S.bq[(K - D) & 3];
+				S.acc = fma_rn(o.y, bb.y, fma_rn(o.x, bb.x, S.acc));
+			}
+		}
 	}
 	// ---- residual of row rho = t-D-2 from stage D.  It lags the stages by one more row so that all its inputs (rows
 	// rho-1 .. rho+1 of stage D and the neighbours of row rho, fetched during the previous step) predate this step:
 	// the residual is off the dependent chain stage 1 -> ... -> stage D of the step.
 	double2 res = make_double2(0.0, 0.0);
-	if (POST != POST_NONE) {
+	if (POST == POST_RESTRICT || POST == POST_NORM) {
 		const int rho = t - D - 2;
 		const int g = F.i0 + rho;
 		Coef cf = B.cu;
@@ -462,7 +468,7 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 		const int tl = t0 + ((t1 - t0) & ~3) + 3;
 		for (int i = tl + 1; i <= tl + FJ_PF; ++i) jf_arrived<MASK>(B, i);
 	}
-	if (POST == POST_NORM) {
+	if (POST == POST_NORM || POST == POST_DOT) {
 		const double s = block_sum<FJ_THREADS>(S.acc);
 		if (B.tid == 0) A.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 	}

@@ -123,7 +123,33 @@ struct TailArgs {
 	int *status, *status_host;
 	long long spin_limit;
 	int do_push, do_wait;
+	int post_op;                                    // TAIL_*: CG scalars derived on the device from the reduced value
 };
+// scal[] slots of the CG recurrences (KSPSolve_CG: beta = z'r, b = beta / betaold, dpi = p'w, a = beta / dpi); they are
+// derived where the dot products finish, so that the vector kernels read them from HBM and the host reads only ||r||
+#define SC_BETA 16
+#define SC_BETAOLD 17
+#define SC_RATIO 18
+#define SC_DPI 19
+#define SC_ALPHA 20
+enum { TAIL_NONE = 0, TAIL_BETA = 1, TAIL_DPI = 2 };
+
+__device__ __forceinline__ void tail_finish(const TailArgs &a, double v)
+{
+	a.scal[a.slot] = v;
+	if (a.host) a.host[a.slot] = v;
+	if (a.post_op == TAIL_BETA) {
+		const double old = a.scal[SC_BETA];           // +inf before the first iteration: ratio 0, p = z + 0 p
+		const double ratio = v / old;
+		a.scal[SC_BETAOLD] = old; a.scal[SC_BETA] = v; a.scal[SC_RATIO] = ratio;
+		if (a.host) { a.host[SC_BETAOLD] = old; a.host[SC_BETA] = v; a.host[SC_RATIO] = ratio; }
+	} else if (a.post_op == TAIL_DPI) {
+		const double al = a.scal[SC_BETA] / v;
+		a.scal[SC_DPI] = v; a.scal[SC_ALPHA] = al;
+		if (a.host) { a.host[SC_DPI] = v; a.host[SC_ALPHA] = al; }
+	}
+	if (a.host) __threadfence_system();
+}
 
 __global__ void __launch_bounds__(1024)
 k_reduce_tail(TailArgs a)
@@ -136,9 +162,7 @@ k_reduce_tail(TailArgs a)
 	}
 	if (threadIdx.x != 0) return;
 	if (a.nranks <= 1) {
-		const double v = a.take_sqrt ? sqrt(s) : s;
-		a.scal[a.slot] = v;
-		if (a.host) { a.host[a.slot] = v; __threadfence_system(); }
+		tail_finish(a, a.take_sqrt ? sqrt(s) : s);
 		return;
 	}
 	if (a.do_push) {
@@ -166,11 +190,11 @@ k_reduce_tail(TailArgs a)
 		const double *sl = a.my_slots + ((v & 1ull) ? a.parity_stride : 0ull);
 		double t = 0.0;
 		for (int r = 0; r < a.nranks; ++r) t += *(volatile const double *)(sl + r * 4);
-		const double o = a.take_sqrt ? sqrt(t) : t;
-		a.scal[a.slot] = o;
-		if (a.host) { a.host[a.slot] = o; __threadfence_system(); }
+		tail_finish(a, a.take_sqrt ? sqrt(t) : t);
 	}
 }
+
+__global__ void k_set_scalar(double *p, double v) { *p = v; }
 
 // keeps a channel's version counter in step on a rank that takes no part in a transfer done inside a compute kernel
 __global__ void k_bump(unsigned long long *ver) { *ver = *ver + 1ull; }

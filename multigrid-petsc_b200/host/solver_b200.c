@@ -282,7 +282,8 @@ static void solve_pcmg(Solver *solver)
 		if (p.coarse_smoother.type < 0) refuse("-mg_coarse_ksp_type richardson needs -mg_coarse_pc_type jacobi|sor");
 	} else refuse("cycle 8: coarse solver must be preonly+lu (default) or richardson+jacobi|sor");
 
-	{ int fuse = 1, bottom = 1; pbopt_get_int("-mgb_fuse", &fuse); pbopt_get_int("-mgb_bottom", &bottom); p.no_fuse = !fuse; p.no_bottom = !bottom; }
+	{ int fuse = 1, bottom = 1, graph = 1; pbopt_get_int("-mgb_fuse", &fuse); pbopt_get_int("-mgb_bottom", &bottom); pbopt_get_int("-mgb_graph", &graph);
+	  p.no_fuse = !fuse; p.no_bottom = !bottom; p.no_graph = !graph; }
 	int iters = 0, reason = 0; double seconds = 0.0;
 	if (mgb_solve_pcmg(e, &p, solver->rnorm, &iters, &reason, &seconds) != MGB_OK) die("mgb_solve_pcmg");
 	solver->numIter = iters;

@@ -23,7 +23,7 @@ int main(void) {
 	O(mgb_vcycle_params, use_graph); O(mgb_vcycle_params, no_fuse); O(mgb_vcycle_params, no_bottom);
 	S(mgb_pcmg_params); O(mgb_pcmg_params, rtol); O(mgb_pcmg_params, max_iter); O(mgb_pcmg_params, level_smoother);
 	O(mgb_pcmg_params, level_its); O(mgb_pcmg_params, coarse); O(mgb_pcmg_params, coarse_smoother); O(mgb_pcmg_params, coarse_its);
-	O(mgb_pcmg_params, no_fuse); O(mgb_pcmg_params, no_bottom);
+	O(mgb_pcmg_params, no_fuse); O(mgb_pcmg_params, no_bottom); O(mgb_pcmg_params, no_graph);
 	S(pb200_result); O(pb200_result, error); O(pb200_result, solve_seconds); O(pb200_result, levels); O(pb200_result, gpu_launches);
 	printf("MGB_IPC_HANDLE_BYTES %d\nMGB_NVEC %d\n", MGB_IPC_HANDLE_BYTES, MGB_NVEC);
 	return 0;

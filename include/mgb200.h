@@ -69,6 +69,9 @@ typedef struct mgb_engine mgb_engine;
 #define MGB_SMOOTH_JACOBI  0  /* -pc_type jacobi : x += scale * D^{-1} (b - A x)                            */
 #define MGB_SMOOTH_RBSOR   1  /* -pc_type sor on the red-black numbering (-map 3): PETSc MatSOR semantics,
                                  reds ((i+j) even) before blacks                                             */
+#define MGB_SMOOTH_LEXSOR  2  /* -pc_type sor on the natural numbering (-map 0,1,2): PETSc's lexicographic MatSOR, run as
+                                 anti-diagonal wavefronts -- same operations, same order, same bits (csrc/mgb_wave.cuh)       */
+#define MGB_SMOOTH_ILU0    3  /* PETSc's default PC (no -pc_type): ILU(0) + triangular solves, also as wavefronts             */
 #define MGB_SOR_SYMMETRIC  0  /* SOR_LOCAL_SYMMETRIC_SWEEP (PCSOR default): forward then backward           */
 #define MGB_SOR_FORWARD    1
 #define MGB_SOR_BACKWARD   2

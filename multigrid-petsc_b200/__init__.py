@@ -24,7 +24,7 @@ DRIVER_BIN = os.path.join(LIB_DIR, "poisson_b200")
 
 VEC_B, VEC_U, VEC_R, VEC_W, VEC_P, VEC_Z, VEC_Q = range(7)
 MAT_A, MAT_RES, MAT_PRO = range(3)
-SMOOTH_JACOBI, SMOOTH_RBSOR = 0, 1
+SMOOTH_JACOBI, SMOOTH_RBSOR, SMOOTH_LEXSOR, SMOOTH_ILU0 = 0, 1, 2, 3
 SOR_SYMMETRIC, SOR_FORWARD, SOR_BACKWARD = 0, 1, 2
 KSP_RICHARDSON, KSP_CG = 0, 1
 IPC_HANDLE_BYTES = 64
@@ -141,6 +141,16 @@ def jacobi(scale=1.0):
 
 def rbsor(omega=1.0, sweep=SOR_SYMMETRIC, its=1):
     return Smoother(SMOOTH_RBSOR, 1.0, omega, sweep, its)
+
+
+def lexsor(omega=1.0, sweep=SOR_SYMMETRIC, its=1):
+    """-pc_type sor on the natural numbering: PETSc's lexicographic MatSOR (wavefront kernels, one GPU)"""
+    return Smoother(SMOOTH_LEXSOR, 1.0, omega, sweep, its)
+
+
+def ilu0(scale=1.0):
+    """PETSc's default PC: ILU(0) inside Richardson (wavefront kernels, one GPU)"""
+    return Smoother(SMOOTH_ILU0, scale, 1.0, SOR_SYMMETRIC, 1)
 
 
 class Engine:

@@ -29,6 +29,7 @@
 #include "mgb_halo.cuh"
 #include "mgb_fused.cuh"
 #include "mgb_coarse_cycle.cuh"
+#include "mgb_wave.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -98,6 +99,8 @@ struct SLevel {                              // one level on one strip
 	double *coef = nullptr;                  // device copy of LevelGeom::coef_host (all global rows)
 	Csr A, R, P;
 	BandLU lu;
+	double *ilu = nullptr;                    // ILU(0) of A[l]: inverted pivots, S multipliers, W multipliers (3 x ni x pitch), lazily
+	bool ilu_valid = false;
 };
 
 struct Strip {
@@ -109,6 +112,7 @@ struct Strip {
 	double *partial = nullptr; size_t partial_cap = 0;
 	double *scal = nullptr, *scal_host = nullptr, *scal_host_dev = nullptr;   // device scalars, mapped pinned mirror (+ its device alias)
 	double *tab_x = nullptr, *tab_y = nullptr;
+	int *wave_progress = nullptr;            // per-panel row counters of the wavefront sweeps (mgb_wave.cuh)
 	int *status_host = nullptr, *status_host_dev = nullptr;   // mapped pinned: a timed-out wait is visible to the host without a copy
 	double *stage_in = nullptr, *stage_out = nullptr;     // dense staging buffers for PCIe copies of large vectors (lazy)
 	size_t stage_cap = 0;
@@ -278,7 +282,8 @@ extern "C" int mgb_destroy(mgb_engine *e)
 	for (int r = 0; r < MGB_MAX_RANKS; ++r) if (e->peer_opened[r]) cudaIpcCloseMemHandle(e->arena_of[r]);
 	for (size_t i = 0; i < e->strips.size(); ++i) {
 		Strip &s = e->strips[i];
-		for (auto &L : s.lev) { cudaFree(L.coef); free_csr(L.A); free_csr(L.R); free_csr(L.P); bandlu_free(L.lu); }
+		for (auto &L : s.lev) { cudaFree(L.coef); free_csr(L.A); free_csr(L.R); free_csr(L.P); bandlu_free(L.lu); cudaFree(L.ilu); }
+		cudaFree(s.wave_progress);
 		cudaFree(s.stage_in); cudaFree(s.stage_out);
 		cudaFree(s.arena); cudaFree(s.partial); cudaFree(s.scal); cudaFreeHost(s.scal_host); cudaFreeHost(s.status_host);
 		cudaFree(s.tab_x); cudaFree(s.tab_y);
@@ -348,6 +353,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 		CU(cudaHostAlloc(&s.status_host, sizeof(int) * 4, cudaHostAllocMapped));
 		s.status_host[0] = 0;
 		CU(cudaHostGetDevicePointer(&s.status_host_dev, s.status_host, 0));
+		CU(cudaMalloc(&s.wave_progress, sizeof(int) * 160));
 		CU(cudaMalloc(&s.tab_x, sizeof(double) * (size_t)(cfg->nj + 16)));
 		CU(cudaMalloc(&s.tab_y, sizeof(double) * (size_t)(cfg->ni + 16)));
 	}
@@ -497,6 +503,7 @@ extern "C" int mgb_set_level_operator(mgb_engine *e, int level, const double *ro
 	for (auto &s : e->strips) {
 		SLevel &S = s.lev[level];
 		bandlu_free(S.lu);
+		S.ilu_valid = false;
 		if (!S.present) continue;
 		CU(cudaMemcpyAsync(S.coef, g.coef_host.data(), sizeof(double) * g.coef_host.size(), cudaMemcpyHostToDevice, s.stream));
 		CU(cudaStreamSynchronize(s.stream));
@@ -1127,6 +1134,35 @@ static int k_rb(mgb_engine *e, int l, int xv, int bv, int colour, double omega, 
 	return halo(e, l, xv, 2);
 }
 
+
+// ------------------------------------------------------------------------------------------------ lexicographic sweeps (wavefronts)
+// PETSc's natural-order smoothers (-pc_type sor on -map 0,1,2; the default ILU(0)): single GPU, whole level (mgb_wave.cuh)
+static int wave(mgb_engine *e, int l, int op, bool reverse, double *x, const double *b, double *t, double omega)
+{
+	Strip &s = e->strips[0];
+	SLevel &S = s.lev[l];
+	const int panels = cdiv(e->geo[l].nj, WV_T);
+	if (panels > 148) return fail(MGB_EINVAL, "wavefront sweeps need all column panels resident: at most %d columns", 148 * WV_T);
+	CU(cudaMemsetAsync(s.wave_progress, 0, sizeof(int) * panels, s.stream));
+	WaveArgs a; memset(&a, 0, sizeof a);
+	a.op = op; a.reverse = reverse ? 1 : 0; a.L = ldev(e, s, l); a.x = x; a.b = b; a.t = t; a.omega = omega;
+	if (S.ilu) { const size_t n = (size_t)S.ni * e->geo[l].pitch; a.invd = S.ilu; a.mS = S.ilu + n; a.mW = S.ilu + 2 * n; }
+	a.progress = s.wave_progress; a.spin_limit = e->spin_limit; a.status = status_of(e, s);
+	k_wave<<<panels, WV_T, 0, s.stream>>>(a);
+	LAUNCHED(e); KCHECK();
+	return MGB_OK;
+}
+static int ilu_factor(mgb_engine *e, int l)
+{
+	SLevel &S = e->strips[0].lev[l];
+	if (S.ilu_valid) return MGB_OK;
+	const size_t n = (size_t)S.ni * e->geo[l].pitch;
+	if (!S.ilu) { CU(cudaMalloc(&S.ilu, sizeof(double) * 3 * n)); CU(cudaMemsetAsync(S.ilu, 0, sizeof(double) * 3 * n, e->strips[0].stream)); }
+	TRY(wave(e, l, WV_ILU_FACTOR, false, nullptr, nullptr, nullptr, 1.0));
+	S.ilu_valid = true;
+	return MGB_OK;
+}
+
 static void swap_vec(mgb_engine *e, int l, int a, int b)
 {
 	for (auto &s : e->strips) {
@@ -1199,6 +1235,45 @@ static int smooth(mgb_engine *e, int l, const mgb_smoother *sm, int its, bool gu
 		}
 		return MGB_OK;
 	}
+	if (sm->type == MGB_SMOOTH_LEXSOR) {
+		// PCApplyRichardson_SOR (scale == 1): MatSOR with its * pc_its * lits sweeps in the natural numbering; a zero initial
+		// guess is the general sweep on x = 0 (the terms MatSOR skips are products with zero)
+		if (sm->scale != 1.0) return fail(MGB_EINVAL, "lexicographic SOR needs -ksp_richardson_scale 1 (PCApplyRichardson_SOR path)");
+		SLevel &S = e->strips[0].lev[l];
+		if (guess_zero) TRY(vec_zero(e, xv, l));
+		const int total = its * (sm->sor_its > 0 ? sm->sor_its : 1);
+		for (int k = 0; k < total; ++k) {
+			if (sm->sor_sweep == MGB_SOR_SYMMETRIC) {
+				TRY(wave(e, l, WV_SOR_FWD, false, S.v[xv], S.v[bv], S.v[sv], sm->omega));      // t = b - L x in the scratch vector
+				TRY(wave(e, l, WV_SOR_BWD_T, true, S.v[xv], S.v[bv], S.v[sv], sm->omega));
+			} else if (sm->sor_sweep == MGB_SOR_FORWARD) {
+				TRY(wave(e, l, WV_SOR_FWD, false, S.v[xv], S.v[bv], nullptr, sm->omega));
+			} else if (sm->sor_sweep == MGB_SOR_BACKWARD) {
+				TRY(wave(e, l, WV_SOR_BWD_B, true, S.v[xv], S.v[bv], nullptr, sm->omega));
+			} else return fail(MGB_EINVAL, "unknown sor_sweep %d", sm->sor_sweep);
+		}
+		return MGB_OK;
+	}
+	if (sm->type == MGB_SMOOTH_ILU0) {
+		// KSPSolve_Richardson, general path (PCILU has no PCApplyRichardson), KSP_NORM_NONE:
+		// r = b - A x (r = b from a zero guess); repeat: z = (LU)^-1 r ; x += scale z ; r = b - A x (skipped after the last)
+		SLevel &S = e->strips[0].lev[l];
+		// work vector for r: the level's residual vector, or -- when the PCMG preconditioner smooths on (r, z) of the outer
+		// Krylov method on the finest level -- the Krylov vector Q (= A p, dead between the CG update and the next A p)
+		const int rv = (bv == MGB_VEC_R || xv == MGB_VEC_R || sv == MGB_VEC_R) ? MGB_VEC_Q : MGB_VEC_R;
+		if (rv == MGB_VEC_Q && (l != 0 || bv == rv || xv == rv || sv == rv)) return fail(MGB_EINVAL, "ILU(0) smoothing: no free work vector on level %d", l);
+		TRY(ilu_factor(e, l));
+		if (guess_zero) { TRY(vec_zero(e, xv, l)); TRY(k_vecop<2>(e, l, rv, bv, 0.0)); }
+		else TRY(k_residual(e, l, xv, bv, rv));
+		for (int k = 0; k < its; ++k) {
+			TRY(k_vecop<2>(e, l, sv, rv, 0.0));                                        // z <- r, solved in place
+			TRY(wave(e, l, WV_ILU_FWD, false, S.v[sv], nullptr, nullptr, 1.0));
+			TRY(wave(e, l, WV_ILU_BWD, true, S.v[sv], nullptr, nullptr, 1.0));
+			TRY(k_vecop<0>(e, l, xv, sv, sm->scale));                                  // x <- x + scale z
+			if (k + 1 < its) TRY(k_residual(e, l, xv, bv, rv));
+		}
+		return MGB_OK;
+	}
 	return fail(MGB_EINVAL, "unknown smoother type %d", sm->type);
 }
 
@@ -1208,6 +1283,17 @@ static int check_smoother(mgb_engine *e, const mgb_smoother *s)
 	if (s->type == MGB_SMOOTH_RBSOR) {
 		if (s->omega <= 0.0 || s->omega >= 2.0) return fail(MGB_EINVAL, "SOR omega must be in (0,2)");
 		TRY(set_sor_omega(e, s->omega));
+	} else if (s->type == MGB_SMOOTH_LEXSOR || s->type == MGB_SMOOTH_ILU0) {
+		if (e->cfg.red_black_numbering) return fail(MGB_EINVAL, "lexicographic SOR / ILU(0) belong to the natural numbering (-map 0,1,2)");
+		if (e->P > 1) return fail(MGB_EINVAL, "lexicographic SOR / ILU(0) are sequential across grid rows: they run on one GPU (PETSc's parallel "
+		                          "versions are processor-local and give other numbers); use Jacobi or -map 3 red-black SOR on strips");
+		if (s->type == MGB_SMOOTH_LEXSOR) {
+			if (s->omega <= 0.0 || s->omega >= 2.0) return fail(MGB_EINVAL, "SOR omega must be in (0,2)");
+			TRY(set_sor_omega(e, s->omega));
+		} else {
+			// factor every level now: allocations are not allowed later, inside a graph capture
+			for (int l = 0; l < e->L; ++l) if (e->geo[l].coef_set) TRY(ilu_factor(e, l));
+		}
 	} else if (s->type != MGB_SMOOTH_JACOBI) return fail(MGB_EINVAL, "unknown smoother type %d", s->type);
 	return MGB_OK;
 }

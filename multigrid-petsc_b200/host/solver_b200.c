@@ -14,12 +14,14 @@
  *
  * Solver options are read from the options database exactly where the reference's KSPSetFromOptions calls
  * would read them (un-prefixed keys for cycle 0, mg_levels_ / mg_coarse_ prefixes for cycle 8).
- * Supported: -pc_type jacobi (any -ksp_richardson_scale) ; -pc_type sor together with -map 3 (red-black
- * numbering; -pc_sor_omega, -pc_sor_its, -pc_sor_lits, -pc_sor_forward/backward/symmetric) ; -ksp_max_it ;
+ * Supported: -pc_type jacobi (any -ksp_richardson_scale) ; -pc_type sor (-pc_sor_omega, -pc_sor_its, -pc_sor_lits,
+ * -pc_sor_forward/backward/symmetric): PETSc's lexicographic MatSOR on the natural numbering (wavefront kernels, one GPU)
+ * or the same arithmetic on the red-black numbering with -map 3 ; -pc_type ilu or NO -pc_type: PETSc's default ILU(0)
+ * (wavefront kernels, one GPU) -- the shipped poisson.in runs unmodified ; -ksp_max_it ;
  * cycle 8: -ksp_type richardson|cg, -ksp_rtol, -ksp_atol, -ksp_divtol, -ksp_max_it, -mg_levels_*, -mg_coarse_*.
  * Extensions: -rtol (cycle-0 tolerance, 1e-7 in the reference), -mgb_graph 0|1, -mgb_csr 0|1.
- * Everything else on this path (PETSc's default ILU(0), lexicographic SOR on the natural numbering, Chebyshev,
- * the research cycles 1-7, 9, 10, several grids per level) is refused with a message, never approximated.
+ * Everything else on this path (Chebyshev, the research cycles 1-7, 9, 10, several grids per level) is refused with a
+ * message, never approximated.
  */
 #include "pb_api.h"
 #include "mgb200.h"
@@ -180,11 +182,14 @@ static void read_smoother(const char *prefix, int rb_numbering, mgb_smoother *s,
 	snprintf(key, sizeof key, "-%spc_type", prefix);
 	pbopt_get_string(key, pc, sizeof pc);
 	if (!strcmp(pc, "jacobi")) s->type = MGB_SMOOTH_JACOBI;
+	else if (!strcmp(pc, "ilu")) {
+		if (rb_numbering) refuse("-pc_type ilu is offered on the natural numbering (-map 0,1,2) only");
+		s->type = MGB_SMOOTH_ILU0;                     /* ILU(0), natural ordering: PETSc's defaults */
+	}
 	else if (!strcmp(pc, "sor")) {
-		if (!rb_numbering)
-			refuse("-pc_type sor on the natural numbering is PETSc's lexicographic SOR, which is inherently sequential; "
-			       "use -map 3 (red-black numbering, same MatSOR arithmetic) or -pc_type jacobi");
-		s->type = MGB_SMOOTH_RBSOR;
+		/* natural numbering: PETSc's lexicographic MatSOR as anti-diagonal wavefronts (same operations, same order);
+		 * -map 3: the same MatSOR arithmetic on the red-black numbering (fully parallel) */
+		s->type = rb_numbering ? MGB_SMOOTH_RBSOR : MGB_SMOOTH_LEXSOR;
 		int its = 1, lits = 1;
 		snprintf(key, sizeof key, "-%spc_sor_omega", prefix); pbopt_get_real(key, &s->omega);
 		snprintf(key, sizeof key, "-%spc_sor_its", prefix); pbopt_get_int(key, &its);
@@ -199,7 +204,7 @@ static void read_smoother(const char *prefix, int rb_numbering, mgb_smoother *s,
 		snprintf(key, sizeof key, "-%spc_sor_local_forward", prefix); if (pbopt_get_bool(key)) s->sor_sweep = MGB_SOR_FORWARD;
 	} else if (pc[0] == '\0') s->type = -1;
 	else {
-		snprintf(g_msg, sizeof g_msg, "-%spc_type %s is not available on the B200 engine (have: jacobi, sor with -map 3)", prefix, pc);
+		snprintf(g_msg, sizeof g_msg, "-%spc_type %s is not available on the B200 engine (have: jacobi, sor, ilu)", prefix, pc);
 		refuse(g_msg);
 	}
 }
@@ -216,9 +221,11 @@ static void vcycle_params(Solver *solver, mgb_vcycle_params *pp)
 	read_smoother("", map_style == 3, &p.smoother, &max_it, ksp_type, sizeof ksp_type);
 	if (strcmp(ksp_type, "richardson"))
 		refuse("cycle 0 smooths with KSPRICHARDSON (src/solver.c:1464); other -ksp_type values are not offered");
-	if (p.smoother.type < 0)
-		refuse("no -pc_type given: the reference would then smooth with PETSc's default ILU(0), which the B200 engine "
-		       "does not offer; pass -pc_type jacobi [-ksp_richardson_scale w] or -map 3 -pc_type sor");
+	if (p.smoother.type < 0) {
+		/* no -pc_type: PETSc's default for a sequential AIJ matrix, ILU(0) -- what the shipped poisson.in runs with */
+		if (map_style == 3) refuse("no -pc_type given: PETSc's default ILU(0) is offered on the natural numbering (-map 0,1,2) only");
+		p.smoother.type = MGB_SMOOTH_ILU0;
+	}
 	/* -ksp_max_it, if present, overrides the sweep counts of every level KSP (KSPSetFromOptions comes last) */
 	p.v0 = (max_it >= 0) ? max_it : solver->v[0];
 	p.v1 = (max_it >= 0) ? max_it : solver->v[1];

@@ -173,8 +173,45 @@ def test_red_black_sor_bit_exact_vs_oracle(npts, levels, mesh, extra):
         o.close()
 
 
+@pytest.mark.parametrize("npts,levels,mesh,extra", [
+    (17, 2, 0, "-pc_type sor"), (33, 3, 0, "-pc_type sor -pc_sor_omega 1.3"), (65, 3, 2, "-pc_type sor -pc_sor_forward"),
+    (65, 3, 1, "-pc_type sor -pc_sor_backward -pc_sor_omega 0.9"), (129, 4, 0, "-pc_type sor -pc_sor_its 2"),
+    (257, 2, 0, "-pc_type sor"), (17, 2, 0, ""), (65, 3, 1, "-pc_type ilu -ksp_richardson_scale 0.9"), (257, 2, 0, "-pc_type ilu")])
+def test_lexicographic_smoothers_bit_exact_vs_oracle(npts, levels, mesh, extra):
+    """PETSc's natural-order smoothers as wavefronts (csrc/mgb_wave.cuh): MatSOR forward / backward / symmetric and the default
+    ILU(0) inside Richardson, against the oracle's restatement of MatSOR / PCILU on the same random inputs, bit for bit.
+    257 columns span three column panels (the inter-panel hand-over through HBM)."""
+    opts = base(npts, levels, mesh=mesh) + " " + extra
+    o = Oracle(opts)
+    s = mgb.Session(opts)
+    e = s.engine
+    if "sor" in extra:
+        sm = mgb.lexsor(omega=1.3 if "1.3" in extra else (0.9 if "0.9" in extra else 1.0),
+                        sweep=mgb.SOR_FORWARD if "forward" in extra else (mgb.SOR_BACKWARD if "backward" in extra else mgb.SOR_SYMMETRIC),
+                        its=2 if "its 2" in extra else 1)
+    else:
+        sm = mgb.ilu0(0.9 if "0.9" in extra else 1.0)
+    rng = np.random.default_rng(11)
+    try:
+        for l in range(levels):
+            ni, nj = e.dims(l)
+            x = rng.uniform(-1, 1, (ni, nj))
+            b = rng.uniform(-1, 1, (ni, nj))
+            e.set_vec(mgb.VEC_B, l, b)
+            for nu, gz in ((1, False), (3, False), (3, True), (1, True)):
+                e.set_vec(mgb.VEC_U, l, x)
+                e.smooth(l, sm, nu, gz)
+                x_g = e.get_vec(mgb.VEC_U, l)
+                x_o = o.to_grid(l, o.smooth(l, o.from_grid(l, b), o.from_grid(l, x), nu, gz))
+                assert x_g.tobytes() == x_o.tobytes(), (l, nu, gz)
+    finally:
+        s.close()
+        o.close()
+
+
 # ------------------------------------------------------------------ end to end against the committed goldens
-E2E = ["n17_l2_jacobi", "n17_l2_jacobi23", "n17_l1_jacobi", "n129_l4_jacobi", "n129_l7_jacobi", "n129_l7_jacobi_v21",
+E2E = ["n17_l2_sor", "n17_l2_ilu_default", "n129_l4_sor", "n129_l4_sor_forward",      # PETSc's natural-order smoothers (wavefronts)
+       "n17_l2_jacobi", "n17_l2_jacobi23", "n17_l1_jacobi", "n129_l4_jacobi", "n129_l7_jacobi", "n129_l7_jacobi_v21",
        "n101_l3_jacobi", "n65_l4_mesh1_jacobi", "n65_l4_mesh2_jacobi", "n129_l7_cg_mg", "n129_l4_cg_mg_jcoarse",
        "n129_l7_rich_mg_monitor", "n1025_l7_jacobi", "n1025_l10_jacobi",
        "n17_l2_rbsor", "n129_l4_rbsor", "n129_l7_rbsor", "n129_l7_rbsor_w12", "n1025_l7_rbsor"]
@@ -206,7 +243,8 @@ def test_end_to_end_matches_golden(name, graph, tmp_path):
 
 
 @pytest.mark.parametrize("name", ["n129_l4_jacobi", "n129_l7_jacobi", "n101_l3_jacobi", "n65_l4_mesh1_jacobi",
-                                  "n129_l7_rbsor", "n1025_l10_jacobi", "n1025_l7_rbsor"])
+                                  "n129_l7_rbsor", "n1025_l10_jacobi", "n1025_l7_rbsor", "n17_l2_sor", "n129_l4_sor",
+                                  "n17_l2_ilu_default"])
 def test_cycle0_solution_is_bit_exact(name):
     """Cycle 0 with Jacobi / red-black smoothing uses no reduction inside the iteration, so the solution vector
     itself is reproduced bit for bit (only the logged norms differ in summation order)."""
@@ -217,8 +255,9 @@ def test_cycle0_solution_is_bit_exact(name):
 
 
 def test_unsupported_configurations_fail_loudly():
-    for opts in (base(17, 2),                                     # PETSc default PC (ILU) not offered
-                 base(17, 2) + " -pc_type sor",                   # lexicographic SOR not offered
+    for opts in (base(17, 2) + " -pc_type lu",                    # a PC the engine does not have
+                 base(129, 4) + " -pc_type sor -mgb_ranks 2 -mgb_emulate 1 -mgb_agglomerate 31",   # lexicographic SOR on strips
+                 base(17, 2, mp=3),                               # default ILU(0) on the red-black numbering
                  base(17, 2, cycle=1) + " " + JAC,                # research cycle
                  base(17, 2, cycle=8) + " -ksp_type cg",          # Chebyshev default smoother
                  "-npts 17 -iter 10 -grids 3 -levels 2 " + JAC):

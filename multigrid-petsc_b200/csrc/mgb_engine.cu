@@ -146,6 +146,7 @@ struct mgb_engine {
 	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
 	int bcast_done = -1;                     // level whose result a fused leg has just broadcast from inside the kernel
 	bool dead = false;                       // a ghost-row wait timed out: the ranks' version counters are out of step, the engine is unusable
+	int rb_fuse_min_rows = 2047;             // red-black SOR: levels with fewer rows take the one-sweep kernels (fuse_level; MGB_RB_FUSE_MIN_ROWS)
 	bool inkernel = true;                    // fused legs push / wait for their strip-to-strip rows themselves (MGB_INKERNEL_HALO=0: separate k_xfer launches)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
@@ -360,6 +361,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	CU(cudaStreamSynchronize(e->strips[0].stream));
 	e->connected = (P == 1) || nlocal > 1;
 	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
+	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }
 
@@ -1368,7 +1370,7 @@ static LevelDev fused_ldev(const mgb_engine *e, const Strip &s, int l)
 	return d;
 }
 
-template <int D, int PRE, int POST>
+template <int D, int PRE, int POST, int SMK = 0>
 static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st)
 {
 	// > 48 KB of dynamic shared memory needs the opt-in once per kernel AND per device (a function attribute lives in
@@ -1380,21 +1382,22 @@ static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st)
 	{
 		std::lock_guard<std::mutex> lk(mu);
 		if (dev >= 0 && dev < 64 && !optin[dev]) {
-			if (cudaFuncSetAttribute(k_jfused<D, PRE, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jf_smem_bytes<D>()) == cudaSuccess)
+			if (cudaFuncSetAttribute(k_jfused<D, PRE, POST, SMK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jf_smem_bytes<D>()) == cudaSuccess)
 				optin[dev] = true;                 // on failure the launch below reports the error through KCHECK
 		}
 	}
-	k_jfused<D, PRE, POST><<<grid, FJ_THREADS, jf_smem_bytes<D>(), st>>>(a);
+	k_jfused<D, PRE, POST, SMK><<<grid, FJ_THREADS, jf_smem_bytes<D>(), st>>>(a);
 }
 
-template <int D>
+template <int D, int SMK = 0>
 static int dispatch_jfused(int pre, int post, const FusedArgs &a, dim3 grid, cudaStream_t st)
 {
-#define JF(PRE_, POST_) if (pre == PRE_ && post == POST_) { launch_jfused<D, PRE_, POST_>(a, grid, st); return MGB_OK; }
+#define JF(PRE_, POST_) if (pre == PRE_ && post == POST_) { launch_jfused<D, PRE_, POST_, SMK>(a, grid, st); return MGB_OK; }
 	JF(PRE_GIVEN, POST_NONE) JF(PRE_GIVEN, POST_RESTRICT) JF(PRE_GIVEN, POST_NORM)
 	JF(PRE_ZERO, POST_NONE) JF(PRE_ZERO, POST_RESTRICT) JF(PRE_ZERO, POST_NORM)
 	JF(PRE_PROLONG, POST_NONE) JF(PRE_PROLONG, POST_NORM)
-	JF(PRE_PROLONG_MULTADD, POST_NONE) JF(PRE_PROLONG_MULTADD, POST_DOT)
+	JF(PRE_PROLONG_MULTADD, POST_NONE)
+	if (SMK == 0) { JF(PRE_PROLONG_MULTADD, POST_DOT) }
 #undef JF
 	return fail(MGB_EINVAL, "fused kernel: combination pre %d / post %d not built", pre, post);
 }
@@ -1437,7 +1440,42 @@ static int restrict_streamed(mgb_engine *e, int l, int bv, int xv)
 	return MGB_OK;
 }
 
-static bool fusable(const mgb_engine *e, const mgb_smoother *sm) { return sm->type == MGB_SMOOTH_JACOBI && !e->cfg.red_black_numbering; }
+// Jacobi on the natural numbering, or red-black SOR (-map 3) in the sweep orders that use k_rb_half's variant 0
+static bool fusable(const mgb_engine *e, const mgb_smoother *sm)
+{
+	if (sm->type == MGB_SMOOTH_JACOBI) return !e->cfg.red_black_numbering;
+	if (sm->type == MGB_SMOOTH_RBSOR)
+		return e->cfg.red_black_numbering && sm->scale == 1.0 && (sm->sor_sweep == MGB_SOR_SYMMETRIC || sm->sor_sweep == MGB_SOR_FORWARD);
+	return false;
+}
+// Does the fused leg pay on level l?  Jacobi: always (3 sweeps + residual + transfer in one pass, and the persistent bottom
+// kernel below 64 rows).  Red-black SOR: a V(3,3) leg is 7 half sweeps = 3 passes of the fused kernel; that beats 7 + 1
+// one-sweep launches only where the level is bandwidth-bound (at 1023 rows and below the data sits in L2 and a one-sweep
+// launch costs ~3 us against 8-20 us of pipeline latency per fused pass).  On strips the distributed levels are fused
+// (their ghost rows travel inside the kernels), the agglomerated ones follow the same size rule on rank 0.
+static bool fuse_level(const mgb_engine *e, const mgb_smoother *sm, int l)
+{
+	if (sm->type != MGB_SMOOTH_RBSOR) return true;
+	if (e->P > 1) return e->geo[l].dist;
+	return e->geo[l].gni >= e->rb_fuse_min_rows;
+}
+// the stages of one smoothing call: `its` Jacobi sweeps (colour -1) or the half sweeps of MatSOR on the red-first numbering
+// in the order smooth() launches them (0 red, 1 black)
+static std::vector<int> smoother_stages(const mgb_smoother *sm, int its)
+{
+	std::vector<int> st;
+	if (sm->type == MGB_SMOOTH_JACOBI) { st.assign(its, -1); return st; }
+	const int total = its * (sm->sor_its > 0 ? sm->sor_its : 1);
+	for (int k = 0; k < total; ++k) {
+		if (sm->sor_sweep == MGB_SOR_SYMMETRIC) {
+			if (!(k > 0 && sm->omega == 1.0)) st.push_back(0);     // a red half sweep right after a red one recomputes the same values
+			st.push_back(1);
+			if (sm->omega != 1.0) st.push_back(1);
+			st.push_back(0);
+		} else { st.push_back(0); st.push_back(1); }
+	}
+	return st;
+}
 
 // One leg on level l: [x += pro * u[l+1]] -> `its` Jacobi sweeps on (b = bv, x = xv) -> [b[l+1] = res * (b - A x)] or
 // [scal[norm_slot] = ||b - A x||].  Sweeps beyond FJ_MAXD are chained as extra passes.  On return the iterate is in v[xv]
@@ -1570,6 +1608,9 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 {
 	const LevelGeom &g = e->geo[l];
 	if (its < 1) return fail(MGB_EINVAL, "fused leg needs at least one sweep");
+	const std::vector<int> stages = smoother_stages(sm, its);
+	const bool rb = sm->type == MGB_SMOOTH_RBSOR;
+	its = (int)stages.size();
 	int done = 0;
 	while (done < its) {
 		const int D = (its - done > FJ_MAXD) ? FJ_MAXD : its - done;
@@ -1589,7 +1630,8 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			SLevel &S = s.lev[l];
 			FusedArgs a; memset(&a, 0, sizeof a);
 			a.u_in = S.v[xv]; a.b = S.v[bv]; a.u_out = S.v[sv];
-			a.F = fused_ldev(e, s, l); a.scale = sm->scale; a.gni = g.gni;
+			a.F = fused_ldev(e, s, l); a.scale = rb ? sm->omega : sm->scale; a.gni = g.gni;
+			for (int k = 0; k < D; ++k) if (stages[done + k] == 1) a.rbmask |= 1 << k;
 			a.rows = pick_rows(g, S.ni);
 			a.R3 = e->R3; a.P3 = e->P3;
 			int tiles = cdiv(g.pitch, FJ_VALID);
@@ -1611,10 +1653,13 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			}
 			if (inkernel) fused_comm(e, s, l, D, pre_k, post_k, bv, xv, S.phys[sv], bcast_k, grid, a);
 			int rc;
-			switch (D) {
+			switch (D + (rb ? 10 : 0)) {
 			case 1: rc = dispatch_jfused<1>(pre_k, post_k, a, grid, s.stream); break;
 			case 2: rc = dispatch_jfused<2>(pre_k, post_k, a, grid, s.stream); break;
-			default: rc = dispatch_jfused<3>(pre_k, post_k, a, grid, s.stream); break;
+			case 3: rc = dispatch_jfused<3>(pre_k, post_k, a, grid, s.stream); break;
+			case 11: rc = dispatch_jfused<1, 1>(pre_k, post_k, a, grid, s.stream); break;
+			case 12: rc = dispatch_jfused<2, 1>(pre_k, post_k, a, grid, s.stream); break;
+			default: rc = dispatch_jfused<3, 1>(pre_k, post_k, a, grid, s.stream); break;
 			}
 			TRY(rc);
 			LAUNCHED(e); KCHECK();
@@ -1821,22 +1866,42 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 	const int Lc = e->L;
 	const mgb_smoother *s = &p->smoother;
 	if (!p->no_fuse && fusable(e, s) && p->v0 >= 1 && (Lc == 1 || p->v1 >= 1)) {
-		// the same cycle with each leg of a level done in one pass (mgb_fused.cuh): identical arithmetic per value
-		const int B = MGB_VEC_B, U = MGB_VEC_U, W = MGB_VEC_W;
+		// the same cycle with each leg of a level done in one pass (mgb_fused.cuh): identical arithmetic per value.  Levels
+		// on which the fused leg does not pay (fuse_level) take the one-kernel-per-operation sequence instead.
+		const int B = MGB_VEC_B, U = MGB_VEC_U, W = MGB_VEC_W, R = MGB_VEC_R;
+		const bool ik = e->P > 1 && e->inkernel;
+		auto FL = [&](int l) { return fuse_level(e, s, l); };
 		if (Lc == 1) {
 			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_NORM, B, U, W, 0));
 		} else {
-			const int lp = p->no_bottom ? Lc : bottom_start(e);   // levels lp .. Lc-1: one persistent launch
-			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));      // :1531-1535
-			for (int l = 1; l < Lc - 1 && l < lp; ++l)
-				TRY(fused_leg(e, l, s, p->v0, PRE_ZERO, POST_RESTRICT, B, U, W, 0));                     // :1534-1536
+			// levels lp .. Lc-1: one persistent launch (Jacobi only)
+			const int lp = (p->no_bottom || s->type != MGB_SMOOTH_JACOBI) ? Lc : bottom_start(e);
+			for (int l = 0; l < Lc - 1 && l < lp; ++l) {                                                    // :1531-1536
+				const bool zero = l > 0 || first;
+				if (FL(l)) TRY(fused_leg(e, l, s, p->v0, zero ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));
+				else {
+					if (ik && l == e->La) TRY(wait_gather(e, l));
+					TRY(smooth(e, l, s, p->v0, zero, B, U, W));
+					TRY(restrict_to_coarse(e, l, B, U, R, true));
+				}
+			}
 			if (lp < Lc) {
-				if (lp == e->La && e->inkernel) TRY(wait_gather(e, lp));   // the bottom kernel consumes the gathered right-hand side
+				if (lp == e->La && ik) TRY(wait_gather(e, lp));        // the bottom kernel consumes the gathered right-hand side
 				TRY(bottom_cycle(e, lp, p->v0, s->scale, p->v1, s->scale, false));
-			} else TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0, true));             // :1536 coarsest
-			for (int l = (lp < Lc ? lp - 1 : Lc - 2); l >= 0; --l) {
-				if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(need_bcast(e, l + 1));
-				TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0, true));  // :1540-1546
+			} else if (FL(Lc - 1)) TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0, true));    // :1536 coarsest
+			else {
+				if (ik && Lc - 1 == e->La) TRY(wait_gather(e, Lc - 1));
+				TRY(smooth(e, Lc - 1, s, p->v1, true, B, U, W));
+			}
+			for (int l = (lp < Lc ? lp - 1 : Lc - 2); l >= 0; --l) {                                           // :1540-1546
+				if (FL(l)) {
+					if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(need_bcast(e, l + 1));
+					TRY(fused_leg(e, l, s, p->v0, PRE_PROLONG, l == 0 ? POST_NORM : POST_NONE, B, U, W, 0, true));
+				} else {
+					TRY(prolong_add(e, l, U, false));
+					TRY(smooth(e, l, s, p->v0, false, B, U, W));
+					if (l == 0) TRY(k_resnorm(e, 0, U, B, 0));
+				}
 			}
 		}
 		TRY(flush_all(e));                                     // scal[0] is already in the mapped host mirror (k_reduce_tail)
@@ -2048,12 +2113,13 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 	// (bottom kernel, LU, one-sweep kernels) gets a wait launch on rank 0 (harmless when a fused leg follows)
 	if (e->P > 1 && e->inkernel && l == e->La && l >= 1) TRY(wait_gather(e, l));
 	if (l >= 1 && !p->no_fuse && !p->no_bottom && p->coarse == MGB_COARSE_RICHARDSON && fusable(e, &p->level_smoother) &&
-	    fusable(e, &p->coarse_smoother) && p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e) &&
+	    fusable(e, &p->coarse_smoother) && p->level_smoother.type == MGB_SMOOTH_JACOBI && p->coarse_smoother.type == MGB_SMOOTH_JACOBI &&
+	    p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e) &&
 	    bv == MGB_VEC_B && xv == MGB_VEC_U)
 		return bottom_cycle(e, l, p->level_its, p->level_smoother.scale, p->coarse_its, p->coarse_smoother.scale, true);
 	if (l == Lc - 1) {
 		if (p->coarse == MGB_COARSE_RICHARDSON) {
-			if (!p->no_fuse && fusable(e, &p->coarse_smoother) && p->coarse_its >= 1)
+			if (!p->no_fuse && fusable(e, &p->coarse_smoother) && fuse_level(e, &p->coarse_smoother, l) && p->coarse_its >= 1)
 				return fused_leg(e, l, &p->coarse_smoother, p->coarse_its, PRE_ZERO, POST_NONE, bv, xv, MGB_VEC_W, 0, true);
 			return smooth(e, l, &p->coarse_smoother, p->coarse_its, true, bv, xv, MGB_VEC_W);
 		}
@@ -2066,11 +2132,11 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 		}
 		return MGB_OK;
 	}
-	if (!p->no_fuse && fusable(e, &p->level_smoother) && p->level_its >= 1) {
+	if (!p->no_fuse && fusable(e, &p->level_smoother) && fuse_level(e, &p->level_smoother, l) && p->level_its >= 1) {
 		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_ZERO, POST_RESTRICT, bv, xv, MGB_VEC_W, 0));
 		TRY(pcmg_cycle(e, p, l + 1, MGB_VEC_B, MGB_VEC_U));
 		if (e->geo[l].dist && !e->geo[l + 1].dist) TRY(need_bcast(e, l + 1));
-		const bool dot = l == 0 && dot_slot >= 0 && dot_done;
+		const bool dot = l == 0 && dot_slot >= 0 && dot_done && p->level_smoother.type == MGB_SMOOTH_JACOBI && p->level_its <= FJ_MAXD;
 		TRY(fused_leg(e, l, &p->level_smoother, p->level_its, PRE_PROLONG_MULTADD, dot ? POST_DOT : POST_NONE, bv, xv, MGB_VEC_W, dot ? dot_slot : 0, true));
 		if (dot) *dot_done = true;
 		return MGB_OK;

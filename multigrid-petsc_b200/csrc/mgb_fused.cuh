@@ -120,15 +120,17 @@ struct FusedArgs {
 	double scale;
 	int rows;                // rows per block (even)
 	int gni;                 // global number of rows of the fine level
+	int rbmask;              // red-black stages (SMK = 1): bit s-1 = colour updated by stage s (0 red = (i+j) even, 1 black); scale = omega
 	FusedComm X;             // all zero on a single strip
 };
 
 struct Coef { double aS, aW, aC, aE, aN, dinv, nS; };   // nS = -aS (power-of-two path)
+template <int SMK = 0>
 __device__ __forceinline__ Coef load_coef(const LevelDev &L, int gni, int grow)
 {
 	const int g = grow < 0 ? 0 : (grow >= gni ? gni - 1 : grow);
 	const double *cf = L.coef + (size_t)g * MGB_COEF_STRIDE;
-	Coef c; c.aS = cf[0]; c.aW = cf[1]; c.aC = cf[2]; c.aE = cf[3]; c.aN = cf[4]; c.dinv = cf[5]; c.nS = -cf[0];
+	Coef c; c.aS = cf[0]; c.aW = cf[1]; c.aC = cf[2]; c.aE = cf[3]; c.aN = cf[4]; c.dinv = cf[SMK ? 6 : 5]; c.nS = -cf[0];   // red-black: idiag = omega / d in the place of 1 / d
 	return c;
 }
 
@@ -170,6 +172,36 @@ __device__ __forceinline__ double2 prolonged_even(double2 u, double amv, double 
 	const double sa = mul(Pw.w[6 + 1], a0v), sb = mul(Pw.w[0 + 1], b0v);
 	if (MULTADD) { e0 = add(add(add(add(u.x, am), a0), bm), b0); e1 = add(add(u.y, sa), sb); }
 	else { e0 = add(u.x, mul(1.0, add(add(add(am, a0), bm), b0))); e1 = add(u.y, mul(1.0, add(sa, sb))); }
+	return make_double2(e0, e1);
+}
+
+// ---- red-black numbering (-map 3): the same transfers with the row sums in ascending RED-FIRST column order, i.e. the
+// arithmetic of k_prolong_add / k_restrict / stencil5_ord with L.rb set.  pm = colour parity of coarse point (I, J0-1):
+// 0 red.  (General arithmetic, no fma: the red-black path is not the headline.)
+template <int MULTADD>
+__device__ __forceinline__ double2 prolonged_odd_rb(double2 u, double cmv, double c0v, const Stencil3 &Pw, int pm)
+{
+	const double cm = mul(Pw.w[3 + 2], cmv), c0 = mul(Pw.w[3 + 0], c0v);
+	const double s0 = mul(Pw.w[3 + 1], c0v);
+	const double t0 = pm ? c0 : cm, t1 = pm ? cm : c0;              // (I, J0-1) black: the red (I, J0) comes first
+	double e0, e1;
+	if (MULTADD) { e0 = add(add(u.x, t0), t1); e1 = add(u.y, s0); }
+	else { e0 = add(u.x, mul(1.0, add(t0, t1))); e1 = add(u.y, mul(1.0, s0)); }
+	return make_double2(e0, e1);
+}
+// pa = colour parity of coarse point (IA, J0-1)
+template <int MULTADD>
+__device__ __forceinline__ double2 prolonged_even_rb(double2 u, double amv, double a0v, double bmv, double b0v, const Stencil3 &Pw, int pa)
+{
+	const double am = mul(Pw.w[6 + 2], amv), a0 = mul(Pw.w[6 + 0], a0v);
+	const double bm = mul(Pw.w[0 + 2], bmv), b0 = mul(Pw.w[0 + 0], b0v);
+	const double sa = mul(Pw.w[6 + 1], a0v), sb = mul(Pw.w[0 + 1], b0v);
+	double t0, t1, t2, t3, s0, s1;
+	if (pa == 0) { t0 = am; t1 = b0; t2 = a0; t3 = bm; s0 = sb; s1 = sa; }   // (IA,J0-1) and (IB,J0) red
+	else         { t0 = a0; t1 = bm; t2 = am; t3 = b0; s0 = sa; s1 = sb; }
+	double e0, e1;
+	if (MULTADD) { e0 = add(add(add(add(u.x, t0), t1), t2), t3); e1 = add(add(u.y, s0), s1); }
+	else { e0 = add(u.x, mul(1.0, add(add(add(t0, t1), t2), t3))); e1 = add(u.y, mul(1.0, add(s0, s1))); }
 	return make_double2(e0, e1);
 }
 
@@ -220,6 +252,32 @@ __device__ __forceinline__ double jf_update(const Coef &cf, double scale, double
 {
 	if (OP == 2) return add(xC, mul(sd, r));              // scale * (r * dinv) == (scale * dinv) * r: r * dinv is exact
 	return add(xC, mul(scale, mul(r, cf.dinv)));
+}
+
+// b - A x with the row sum in red-first order (stencil5_ord): order 1 = red row (diagonal first), 2 = black row (diagonal last)
+template <int OP>
+__device__ __forceinline__ double jf_residual_rb(const Coef &cf, int order, double b, double xS, double xW, double xC, double xE, double xN)
+{
+	if (OP == 2) {
+		// c * fl(...) with the same association as stencil5_ord; -4 xC and c t are exact products (see jf_residual)
+		double t;
+		if (order == 1) t = add(add(add(fma_rn(-4.0, xC, xS), xW), xE), xN);
+		else            t = fma_rn(-4.0, xC, add(add(add(xS, xW), xE), xN));
+		return fma_rn(cf.nS, t, b);
+	}
+	return sub(b, stencil5_ord(order, cf.aS, cf.aW, cf.aC, cf.aE, cf.aN, xS, xW, xC, xE, xN));
+}
+// one point of a red-black half sweep (MatSOR on the red-first numbering, k_rb_half variant 0): cf.dinv holds idiag = omega / d
+template <int OP>
+__device__ __forceinline__ double jf_rb_update(const Coef &cf, double om1, double b, double xS, double xW, double xC, double xE, double xN)
+{
+	double sum = b;
+	if (OP == 2) {
+		sum = fma_rn(cf.nS, xS, sum); sum = fma_rn(cf.nS, xW, sum); sum = fma_rn(cf.nS, xE, sum); sum = fma_rn(cf.nS, xN, sum);
+	} else {
+		sum = sub(sum, mul(cf.aS, xS)); sum = sub(sum, mul(cf.aW, xW)); sum = sub(sum, mul(cf.aE, xE)); sum = sub(sum, mul(cf.aN, xN));
+	}
+	return add(mul(om1, xC), mul(sum, cf.dinv));
 }
 
 // The stencil coefficients are warp-uniform; left to itself the compiler parks them in uniform registers and copies
@@ -275,7 +333,7 @@ __device__ __forceinline__ void jf_arrived(const JfBlock &B, int i)
 	} else cp_async_wait<FJ_PF>();
 }
 
-template <int D, int PRE, int POST, bool MASK, int OP, int K>
+template <int D, int PRE, int POST, bool MASK, int OP, int K, int SMK>
 __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, JfState<D> &S, double (*sh)[D + 2][FJ_PUB],
                                         double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int t)
 {
@@ -298,10 +356,21 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	S.bq[(K + 3) & 3] = *reinterpret_cast<const double2 *>(&in_b[(t - 1 - B.rbase) & (FJ_NR - 1)][2 * tid]);   // slot of row t-1
 	if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) {
 		// t = 4m + K: coarse rows T-1, T, T+1 with T = 2m are in cq[0..2] (fine rows t..t+3 of the group need exactly these)
-		if (K == 0) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[0].x, S.cq[0].y, S.cq[1].x, S.cq[1].y, A.P3);
-		if (K == 1) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[1].x, S.cq[1].y, A.P3);
-		if (K == 2) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[1].x, S.cq[1].y, S.cq[2].x, S.cq[2].y, A.P3);
-		if (K == 3) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[2].x, S.cq[2].y, A.P3);
+		if (SMK == 0) {
+			if (K == 0) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[0].x, S.cq[0].y, S.cq[1].x, S.cq[1].y, A.P3);
+			if (K == 1) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[1].x, S.cq[1].y, A.P3);
+			if (K == 2) u0 = prolonged_even<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[1].x, S.cq[1].y, S.cq[2].x, S.cq[2].y, A.P3);
+			if (K == 3) u0 = prolonged_odd<PRE == PRE_PROLONG_MULTADD, OP == 2>(u0, S.cq[2].x, S.cq[2].y, A.P3);
+		} else {
+			// colour parity of coarse point (I, J0-1) for the first coarse row the fine row touches: I = T-1, T, T, T+1 for K = 0..3
+			const int T = (t - K) >> 1;
+			const int Jm = (B.j0 >> 1) - 1;
+			const int pc = (A.C.i0 + T + (K == 0 ? -1 : (K == 3 ? 1 : 0)) + Jm) & 1;
+			if (K == 0) u0 = prolonged_even_rb<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[0].x, S.cq[0].y, S.cq[1].x, S.cq[1].y, A.P3, pc);
+			if (K == 1) u0 = prolonged_odd_rb<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[1].x, S.cq[1].y, A.P3, pc);
+			if (K == 2) u0 = prolonged_even_rb<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[1].x, S.cq[1].y, S.cq[2].x, S.cq[2].y, A.P3, pc);
+			if (K == 3) u0 = prolonged_odd_rb<PRE == PRE_PROLONG_MULTADD>(u0, S.cq[2].x, S.cq[2].y, A.P3, pc);
+		}
 	}
 	if (MASK) {
 		const bool rk = row_ok(t);
@@ -316,10 +385,23 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 		const int c = t - s;
 		const int g = F.i0 + c;
 		Coef cf = B.cu;
-		if (OP == 0) cf = load_coef(F, A.gni, g);
+		if (OP == 0) cf = load_coef<SMK>(F, A.gni, g);
 		const double2 bb = S.bq[(K - s) & 3];             // b of row t-s
 		double2 o;
-		if (PRE == PRE_ZERO && s == 1) {
+		if (SMK == 1) {
+			// half sweep of one colour: the points of that colour take the MatSOR update from their four neighbours (all of
+			// the other colour, i.e. unchanged by this stage), the others pass through.  .x is column j0 (even): red iff g even
+			const double2 xm = S.win[s - 1][(K - s - 1) & 3], xc = S.win[s - 1][(K - s) & 3], xn = S.win[s - 1][(K - s + 1) & 3];
+			const int colour = (A.rbmask >> (s - 1)) & 1;
+			o = xc;
+			if (((g + colour) & 1) == 0) {
+				const double xw = shp[s - 1][FJ_Y(tid - 1)];
+				o.x = jf_rb_update<OP>(cf, B.scale, bb.x, xm.x, xw, xc.x, xc.y, xn.x);
+			} else {
+				const double xe = shp[s - 1][FJ_X(tid + 1)];
+				o.y = jf_rb_update<OP>(cf, B.scale, bb.y, xm.y, xc.x, xc.y, xe, xn.y);
+			}
+		} else if (PRE == PRE_ZERO && s == 1) {
 			// first Richardson iteration from a zero guess: r = b, x = 0 + scale * (r * dinv)
 			o.x = (OP == 2) ? mul(B.sd, bb.x) : mul(B.scale, mul(bb.x, cf.dinv));
 			o.y = (OP == 2) ? mul(B.sd, bb.y) : mul(B.scale, mul(bb.y, cf.dinv));
@@ -358,11 +440,17 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 		const int rho = t - D - 2;
 		const int g = F.i0 + rho;
 		Coef cf = B.cu;
-		if (OP == 0) cf = load_coef(F, A.gni, g);
+		if (OP == 0) cf = load_coef<SMK>(F, A.gni, g);
 		const double2 xm = S.win[D][(K - D - 3) & 3], xc = S.win[D][(K - D - 2) & 3], xn = S.win[D][(K - D - 1) & 3];
 		const double2 bb = (D + 2 <= 4) ? S.bq[(K - D - 2) & 3] : bold;
-		res.x = jf_residual<OP>(cf, bb.x, xm.x, S.wer[0], xc.x, xc.y, xn.x);
-		res.y = jf_residual<OP>(cf, bb.y, xm.y, xc.x, xc.y, S.wer[1], xn.y);
+		if (SMK == 1) {
+			const int ox = (g & 1) ? 2 : 1;                // .x (even column) is red iff the global row is even
+			res.x = jf_residual_rb<OP>(cf, ox, bb.x, xm.x, S.wer[0], xc.x, xc.y, xn.x);
+			res.y = jf_residual_rb<OP>(cf, 3 - ox, bb.y, xm.y, xc.x, xc.y, S.wer[1], xn.y);
+		} else {
+			res.x = jf_residual<OP>(cf, bb.x, xm.x, S.wer[0], xc.x, xc.y, xn.x);
+			res.y = jf_residual<OP>(cf, bb.y, xm.y, xc.x, xc.y, S.wer[1], xn.y);
+		}
 		if (MASK) {
 			const bool rok = g >= 0 && g < A.gni;
 			if (!B.in0 || !rok) res.x = 0.0;
@@ -386,7 +474,17 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 			if (B.st_ok && I >= (B.y0 >> 1) && I < (B.y1 >> 1) && I < A.C.ni && J < A.C.pitch) {
 				constexpr int R0 = (RP + 2) & 3, R1 = (RP + 3) & 3;    // rows rp-2, rp-1
 				double sum = mul(A.R3.w[0], S.rw[R0][0]);
-				if (OP == 2) {
+				if (SMK == 1) {
+					// red-first numbering of the fine grid: the five red fine points (a + b even), then the four black ones
+					sum = add(sum, mul(A.R3.w[2], S.rw[R0][2]));
+					sum = add(sum, mul(A.R3.w[4], S.rw[R1][1]));
+					sum = add(sum, mul(A.R3.w[6], S.rw[RP][0]));
+					sum = add(sum, mul(A.R3.w[8], S.rw[RP][2]));
+					sum = add(sum, mul(A.R3.w[1], S.rw[R0][1]));
+					sum = add(sum, mul(A.R3.w[3], S.rw[R1][0]));
+					sum = add(sum, mul(A.R3.w[5], S.rw[R1][2]));
+					sum = add(sum, mul(A.R3.w[7], S.rw[RP][1]));
+				} else if (OP == 2) {
 					// power-of-two weights (1/16, 1/8, 1/4): exact products, add(sum, mul(w, r)) == fma(w, r, sum)
 					sum = fma_rn(A.R3.w[1], S.rw[R0][1], sum);
 					sum = fma_rn(A.R3.w[2], S.rw[R0][2], sum);
@@ -418,7 +516,7 @@ __device__ __forceinline__ void jf_step(const FusedArgs &A, const JfBlock &B, Jf
 	__syncthreads();
 }
 
-template <int D, int PRE, int POST, bool MASK, int OP>
+template <int D, int PRE, int POST, bool MASK, int OP, int SMK>
 __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, double (*sh)[D + 2][FJ_PUB],
                                        double (*in_u)[FJ_COLS], double (*in_b)[FJ_COLS], int t0, int t1)
 {
@@ -457,10 +555,10 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 			const int T = (t >> 1) + 2;                    // the next group of four fine rows needs coarse rows T-1 (held), T, T+1
 			S.cn[0] = load_c(T); S.cn[1] = load_c(T + 1);
 		}
-		jf_step<D, PRE, POST, MASK, OP, 0>(A, B, S, sh, in_u, in_b, t);
-		jf_step<D, PRE, POST, MASK, OP, 1>(A, B, S, sh, in_u, in_b, t + 1);
-		jf_step<D, PRE, POST, MASK, OP, 2>(A, B, S, sh, in_u, in_b, t + 2);
-		jf_step<D, PRE, POST, MASK, OP, 3>(A, B, S, sh, in_u, in_b, t + 3);
+		jf_step<D, PRE, POST, MASK, OP, 0, SMK>(A, B, S, sh, in_u, in_b, t);
+		jf_step<D, PRE, POST, MASK, OP, 1, SMK>(A, B, S, sh, in_u, in_b, t + 1);
+		jf_step<D, PRE, POST, MASK, OP, 2, SMK>(A, B, S, sh, in_u, in_b, t + 2);
+		jf_step<D, PRE, POST, MASK, OP, 3, SMK>(A, B, S, sh, in_u, in_b, t + 3);
 		if (PRE == PRE_PROLONG || PRE == PRE_PROLONG_MULTADD) { S.cq[0] = S.cq[2]; S.cq[1] = S.cn[0]; S.cq[2] = S.cn[1]; }
 	}
 	if (!MASK || B.tma) {
@@ -487,7 +585,7 @@ __device__ __forceinline__ void jf_wait_list(const FusedComm &X, int which, int 
 	}
 }
 
-template <int D, int PRE, int POST>
+template <int D, int PRE, int POST, int SMK>
 __global__ void __launch_bounds__(FJ_THREADS, 4)
 k_jfused(FusedArgs A)
 {
@@ -518,9 +616,11 @@ k_jfused(FusedArgs A)
 	B.ld_ok = B.j0 >= 0 && B.j0 < F.pitch;                // the pair may be loaded (pad columns hold zeros)
 	B.st_ok = B.j0 >= B.c0 && B.j0 < B.c0 + FJ_VALID && B.j0 < F.pitch;
 	{
-		const Coef c = load_coef(F, A.gni, F.i0);         // uniform operator: one coefficient set
+		const Coef c = load_coef<SMK>(F, A.gni, F.i0);    // uniform operator: one coefficient set
 		B.cu.aS = vreg(c.aS); B.cu.aW = vreg(c.aW); B.cu.aC = vreg(c.aC); B.cu.aE = vreg(c.aE); B.cu.aN = vreg(c.aN);
-		B.cu.dinv = vreg(c.dinv); B.cu.nS = vreg(c.nS); B.scale = vreg(A.scale); B.sd = vreg(A.scale * c.dinv);
+		B.cu.dinv = vreg(c.dinv); B.cu.nS = vreg(c.nS);
+		B.scale = vreg(SMK ? sub(1.0, A.scale) : A.scale);    // red-black: 1 - omega (A.scale carries omega)
+		B.sd = vreg(A.scale * c.dinv);
 	}
 	// steps: stage 0 of row y0-D-1 is the first needed, the restriction of row y1 completes at step y1+D+3;
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
@@ -542,12 +642,12 @@ k_jfused(FusedArgs A)
 	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 4 + FJ_PF < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) &&
 	                      (te + 4 + FJ_PF < F.ni + MGB_GHOST_ROWS);
 	if (F.uniform == 2) {
-		if (interior) jf_run<D, PRE, POST, false, 2>(A, B, sh, in_u, in_b, tb, te);
-		else          jf_run<D, PRE, POST, true, 2>(A, B, sh, in_u, in_b, tb, te);
-	} else if (F.uniform == 1) {
-		if (interior) jf_run<D, PRE, POST, false, 1>(A, B, sh, in_u, in_b, tb, te);
-		else          jf_run<D, PRE, POST, true, 1>(A, B, sh, in_u, in_b, tb, te);
-	} else            jf_run<D, PRE, POST, true, 0>(A, B, sh, in_u, in_b, tb, te);
+		if (interior) jf_run<D, PRE, POST, false, 2, SMK>(A, B, sh, in_u, in_b, tb, te);
+		else          jf_run<D, PRE, POST, true, 2, SMK>(A, B, sh, in_u, in_b, tb, te);
+	} else if (F.uniform == 1 && SMK == 0) {
+		if (interior) jf_run<D, PRE, POST, false, 1, SMK>(A, B, sh, in_u, in_b, tb, te);
+		else          jf_run<D, PRE, POST, true, 1, SMK>(A, B, sh, in_u, in_b, tb, te);
+	} else            jf_run<D, PRE, POST, true, 0, SMK>(A, B, sh, in_u, in_b, tb, te);    // (red-black: the general path also for uniform, non-power-of-two operators)
 	// ---- push: the rows of this block that lie in a push range travel to the peers AFTER the row loop (nothing of this is
 	// in the hot loop): every thread re-reads exactly the elements it stored itself, so no fence is needed in between
 	if (A.X.nch) {

@@ -16,6 +16,28 @@ import numpy as np
 _pkg = importlib.import_module("multigrid-petsc_b200")
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores next to GPU `index` (NVML's ideal CPU affinity), so that the pinned host buffers
+    it allocates afterwards live on that socket and its PCIe copies do not cross the inter-socket link -- what
+    `mpiexec --bind-to` / `numactl` do for the reference's ranks.  Best effort: returns the CPU list or None."""
+    if os.environ.get("MGB_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:
+        return None
+
+
 def init_distributed(backend=None):
     """Join the torchrun rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment)."""
     import torch
@@ -24,7 +46,14 @@ def init_distributed(backend=None):
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            try:
+                phys = int(vis.split(",")[local]) if vis else local
+            except ValueError:
+                phys = local
+            bind_to_gpu_numa_node(phys)
         dist.init_process_group(backend=backend)
     return dist.get_rank(), dist.get_world_size()
 
@@ -162,6 +191,16 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn, bench):
         cycles1 += s.solve_rhs(hosts[k % 2][0].data_ptr(), hosts[k % 2][1].data_ptr())["num_iter"]
     torch.cuda.synchronize()
     t_single = _max_over_ranks(time.perf_counter() - t0)
+    # where a single Solve() spends its time: upload of this rank's rows, the cycles, download of its rows (max over ranks)
+    def timed(fn):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+        return 1e3 * _max_over_ranks(time.perf_counter() - t0)
+    bview = hosts[0][0].numpy().reshape(n, n)
+    uview = hosts[0][1].numpy().reshape(n, n)
+    t_up = timed(lambda: e._ck(e.L.mgb_vec_set(e.h, _pkg.VEC_B, 0, _pkg._pd(bview))))
+    t_sv = timed(lambda: e.solve_vcycle(sm, 3, 3, max_iter=1000, rtol=1e-7))
+    t_dn = timed(lambda: e._ck(e.L.mgb_vec_get(e.h, _pkg.VEC_U, 0, _pkg._pd(uview))))
     # (b) the pipelined stream
     dist.barrier()
     torch.cuda.synchronize()
@@ -195,6 +234,8 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn, bench):
                 "e2e": {"value": cycles / t_e2e, "unit": "V-cycles/s", "h2d_bytes_per_step": bytes_per_solve * nsolve / cycles,
                         "d2h_bytes_per_step": bytes_per_solve * nsolve / cycles, "solves": nsolve, "cycles_per_solve": cycles / nsolve,
                         "single_solve_value": cycles1 / t_single,
+                        "single_solve_breakdown_ms": {"upload_rhs_rows": t_up, "cycles_to_1e-7": t_sv, "download_solution_rows": t_dn,
+                                                      "per_rank_bytes_each_way": bytes_per_solve / world},
                         "note": "a stream of right-hand sides (pb200_solve_rhs_many): per solve every rank uploads its rows of the rhs "
                                 "(pinned) + V-cycles to 1e-7 + reads its rows of u, copies overlapping the neighbouring solves; bytes are "
                                 "totals over the ranks, per V-cycle"},

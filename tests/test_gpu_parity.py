@@ -332,6 +332,18 @@ def test_strips_emulated_cycle0_bit_exact(name, ranks, aggl):
     assert np.allclose(r["error"], _hex(g["error_hex"]), rtol=RTOL, atol=0.0)
 
 
+@pytest.mark.parametrize("name", ["n17_l2_rbsor", "n129_l4_rbsor", "n129_l7_rbsor", "n129_l7_rbsor_w12", "n1025_l7_rbsor"])
+def test_red_black_fused_legs_on_every_level(name, monkeypatch):
+    """Red-black SOR normally takes the fused legs on bandwidth-bound levels only (>= 2047 rows on one GPU); with the threshold
+    at 0 every level of the small goldens runs through k_jfused<.., SMK = 1>: same bits."""
+    monkeypatch.setenv("MGB_RB_FUSE_MIN_ROWS", "0")
+    g = GOLD[name]
+    r = mgb.run_poisson(g["options"])
+    assert r["num_iter"] == g["num_iter"]
+    assert np.allclose(r["rnorm"], _hex(g["rnorm_hex"]), rtol=RTOL, atol=RNORM_ATOL)
+    assert hashlib.sha256(np.ascontiguousarray(r["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]
+
+
 @pytest.mark.parametrize("name,ranks,aggl", [("n129_l7_jacobi", 2, 31), ("n129_l7_jacobi", 4, 31), ("n1025_l10_jacobi", 4, 0),
                                              ("n129_l7_cg_mg", 2, 31)])
 def test_strips_emulated_separate_exchange_launches(name, ranks, aggl, monkeypatch):
@@ -427,6 +439,8 @@ def test_strip_configuration_errors():
     base(129, 5, v="4,2") + " " + JAC, base(129, 4, v="6,9", it=200) + " " + JAC, base(101, 3) + " " + JAC,
     base(65, 4, mesh=1, it=400) + " " + JAC, base(65, 4, mesh=2, it=400) + " " + JAC, base(17, 1, it=50) + " " + JAC,
     base(1025, 10) + " " + JAC, base(513, 3, it=30) + " " + JAC,
+    base(2049, 3, it=6, mp=3) + " -pc_type sor",                       # red-black: level 0 fused (3 passes per leg), levels 1-2 one-sweep kernels
+    base(2049, 4, it=5, mp=3) + " -pc_type sor -pc_sor_forward -pc_sor_omega 1.1",
     base(129, 7, cycle=8) + " -ksp_type cg -ksp_rtol 1e-10 -mg_levels_ksp_type richardson -mg_levels_pc_type jacobi "
     "-mg_levels_ksp_richardson_scale 0.8 -mg_levels_ksp_max_it 3",
     base(257, 4, cycle=8, it=60) + " -ksp_type richardson -mg_levels_ksp_type richardson -mg_levels_pc_type jacobi "

@@ -28,6 +28,10 @@ RUNS = [
     ("config1: 1025^2, 7-level V(3,3), Jacobi 0.8", base(1025, 7) + " " + JAC),
     ("config1': 1025^2, 10-level V(3,3), red-black SOR (coarsest 1x1)", base(1025, 10, mp=3) + " " + RB),
     ("config1': 1025^2, 10-level V(3,3), Jacobi 0.8", base(1025, 10) + " " + JAC),
+    ("config1b: 4097^2, 12-level V(3,3), red-black SOR (levels >= 2047 rows: fused legs)", base(4097, 12, mp=3) + " " + RB),
+    ("config1b: 4097^2, 12-level V(3,3), red-black SOR, one-sweep kernels only (-mgb_fuse 0)", base(4097, 12, mp=3) + " " + RB + " -mgb_fuse 0"),
+    ("config1c: 8193^2, 13-level V(3,3), red-black SOR (fused legs on levels 0-2)", base(8193, 13, mp=3) + " " + RB),
+    ("config1c: 8193^2, 13-level V(3,3), red-black SOR, one-sweep kernels only (-mgb_fuse 0)", base(8193, 13, mp=3) + " " + RB + " -mgb_fuse 0"),
     ("config2: 4097^2, MG(12 levels, Jacobi 0.8 x3, LU coarse)-preconditioned CG to 1e-10", base(4097, 12, cycle=8, it=200) + " -ksp_type cg -ksp_rtol 1e-10 " + MGJ),
     # plain V-cycle iteration cannot reach 1e-10 on these grids in fp64: the true residual b - A u stagnates at
     # ~1.6e-10 (4097^2) / ~6.3e-10 (8193^2) of ||b|| (eps * cond); 1e-9 is reachable, 1e-10 needs the CG wrapper,

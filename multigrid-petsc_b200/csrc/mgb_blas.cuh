@@ -14,6 +14,7 @@ template <int OP>
 __global__ void __launch_bounds__(MGB_RED_THREADS)
 k_reduce1(const double *__restrict__ x, const double *__restrict__ y, size_t n2, double *__restrict__ partial)
 {
+	pdl_enter();
 	// n2 = number of double2 elements
 	double acc = 0.0;
 	const size_t stride = (size_t)gridDim.x * MGB_RED_THREADS;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256)
 k_axpy(double *__restrict__ y, const double *__restrict__ x, size_t n2, double alpha,
        const double *__restrict__ alpha_dev, double alpha_sign)
 {
+	pdl_enter();
 	if (alpha_dev) alpha = alpha_sign * alpha_dev[0];
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n2; k += stride) {
@@ -139,20 +141,27 @@ __global__ void k_publish(double *__restrict__ host_mapped, const double *__rest
 
 // The CG vector update in one pass (KSPSolve_CG: VecAXPY(x, a, p); VecAXPY(r, -a, w); VecNorm(r)):
 // x += a p ; r -= a w ; partial[block] = sum r^2.  40 B per unknown instead of 24 + 24 + 8.
+// x == nullptr: the x update is deferred into the next direction step (k_cg_pstep): r -= a w ; ||r|| only, 24 B.
 __global__ void __launch_bounds__(MGB_RED_THREADS)
 k_cg_update(double *__restrict__ x, const double *__restrict__ p, double *__restrict__ r, const double *__restrict__ w,
             size_t n2, double a, double *__restrict__ partial, const double *__restrict__ a_dev)
 {
+	pdl_enter();
 	if (a_dev) a = a_dev[0];                      // alpha = beta / p'w as left by the reduction tail (TAIL_DPI)
 	double acc = 0.0;
 	const double ma = -a;
 	const size_t stride = (size_t)gridDim.x * MGB_RED_THREADS;
 	for (size_t k = (size_t)blockIdx.x * MGB_RED_THREADS + threadIdx.x; k < n2; k += stride) {
-		const double2 xv = ld2(x + 2 * k), pv = ld2(p + 2 * k), rv = ld2(r + 2 * k), wv = ld2(w + 2 * k);
-		double2 xo, ro;
-		xo.x = add(xv.x, mul(a, pv.x)); xo.y = add(xv.y, mul(a, pv.y));
+		const double2 rv = ld2(r + 2 * k), wv = ld2(w + 2 * k);
+		double2 ro;
+		if (x) {
+			const double2 xv = ld2(x + 2 * k), pv = ld2(p + 2 * k);
+			double2 xo;
+			xo.x = add(xv.x, mul(a, pv.x)); xo.y = add(xv.y, mul(a, pv.y));
+			st2(x + 2 * k, xo);
+		}
 		ro.x = add(rv.x, mul(ma, wv.x)); ro.y = add(rv.y, mul(ma, wv.y));
-		st2(x + 2 * k, xo); st2(r + 2 * k, ro);
+		st2(r + 2 * k, ro);
 		acc += ro.x * ro.x + ro.y * ro.y;
 	}
 	const double s = block_sum<MGB_RED_THREADS>(acc);

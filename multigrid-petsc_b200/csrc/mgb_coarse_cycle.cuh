@@ -8,7 +8,8 @@
 //   up:    MatMult(pro) + VecAXPY  ->  KSPSolve (nonzero guess, its sweeps)                  per level
 // These levels hold 1/12 of the unknowns but cost ~20 launches of ~10-30 us each; here the whole thing is a few
 // dozen phases of ~1 us.  The arithmetic per value is that of the one-sweep kernels (same operation order, no FMA),
-// so the results are bit-identical.  Data stays in global memory (L2-resident: <= 0.5 MB per vector); loads use
+// so the results are bit-identical.  Smoothers: weighted Jacobi (out of place, ping-pong) and red-black SOR on the
+// red-first numbering (-map 3; in-place half sweeps, sums in red-first order).  Data stays in global memory (L2-resident: <= 0.5 MB per vector); loads use
 // ld.global.cg so that no stale L1 line of another CTA's output can be read; cluster.sync() orders the phases.
 #pragma once
 #include "mgb_common.cuh"
@@ -25,10 +26,14 @@ struct CLevel {
 	int ni, nj, pitch, uniform;
 	int its_down, its_up;    // sweeps on the way down (zero guess) / up (after the correction); coarsest: its_down only
 	double scale;            // Richardson damping of this level's smoother
+	unsigned mask_down, mask_up;   // red-black SOR: its_* counts HALF sweeps, bit k = colour of half sweep k (0 red, 1 black)
 };
 struct CoarseArgs {
 	int nlev;                // levels lev[0] (finest of the bottom part) .. lev[nlev-1] (coarsest)
 	int multadd;             // 1: PCMG's MatInterpolateAdd order in the correction step
+	int rb;                  // 1: red-black SOR on the red-first numbering (-map 3): in-place half sweeps, row sums and transfer
+	                         //    sums in red-first order (k_rb_half variant 0, k_restrict<1> / k_prolong_add with L.rb)
+	double omega;            // SOR relaxation factor (coef[6] holds omega / diag)
 	CLevel lev[CC_MAXLEV];
 	Stencil3 R3, P3;
 };
@@ -97,8 +102,33 @@ __device__ __forceinline__ void sweep(const CLevel &L, const double *x, double *
 		}
 	}
 }
-// bc = res * (b - A x)   (k_restrict<1>, natural numbering)
+// one red-black half sweep of `colour`, in place (k_rb_half variant 0).  zero: the iterate is taken as zero (the first half
+// sweep of a zero-guess smoothing; the same arithmetic on zeros) and the points of the other colour are set to zero.
 template <bool G>
+__device__ __forceinline__ void rb_half(const CLevel &L, double *x, int colour, double om1, bool zero, const Rows &R)
+{
+	const ptrdiff_t P = L.pitch;
+	for (int i = R.gw; i < L.ni; i += R.GW) {
+		const double *cf = L.coef + (size_t)i * MGB_COEF_STRIDE;
+		const double aS = cf[0], aW = cf[1], aE = cf[3], aN = cf[4], idiag = cf[6];
+		for (int j = R.lane; j < L.pitch; j += 32) {
+			const ptrdiff_t o = (ptrdiff_t)i * P + j;
+			if (j >= L.nj) { if (zero) x[o] = 0.0; continue; }
+			if (((i + j + colour) & 1) == 0) {
+				double xS = 0.0, xW = 0.0, xC = 0.0, xE = 0.0, xN = 0.0;
+				if (!zero) { xS = ld<G>(x + o - P); xW = ld<G>(x + o - 1); xC = ld<G>(x + o); xE = ld<G>(x + o + 1); xN = ld<G>(x + o + P); }
+				double sum = ld<G>(L.b + o);
+				sum = sub(sum, mul(aS, xS));
+				sum = sub(sum, mul(aW, xW));
+				sum = sub(sum, mul(aE, xE));
+				sum = sub(sum, mul(aN, xN));
+				x[o] = add(mul(om1, xC), mul(sum, idiag));
+			} else if (zero) x[o] = 0.0;
+		}
+	}
+}
+// bc = res * (b - A x)   (k_restrict<1>; RB: row sums and the nine-term sum in red-first order)
+template <bool G, bool RB>
 __device__ __forceinline__ void residual_restrict(const CLevel &F, const double *x, const CLevel &C, const Stencil3 &Rw, const Rows &R)
 {
 	const ptrdiff_t P = F.pitch;
@@ -107,6 +137,7 @@ __device__ __forceinline__ void residual_restrict(const CLevel &F, const double 
 			double out = 0.0;
 			if (J < C.nj) {
 				double sum = 0.0;
+				double r[9];
 #pragma unroll
 				for (int a = 0; a < 3; ++a) {
 					const int i = 2 * I + a;
@@ -115,10 +146,22 @@ __device__ __forceinline__ void residual_restrict(const CLevel &F, const double 
 #pragma unroll
 					for (int b = 0; b < 3; ++b) {
 						const ptrdiff_t o = (ptrdiff_t)i * P + (2 * J + b);
-						const double t = stencil5(aS, aW, aC, aE, aN, ld<G>(x + o - P), ld<G>(x + o - 1), ld<G>(x + o), ld<G>(x + o + 1), ld<G>(x + o + P));
-						const double term = mul(Rw.w[a * 3 + b], sub(ld<G>(F.b + o), t));
-						sum = (a == 0 && b == 0) ? term : add(sum, term);
+						if (RB) {
+							// the colour of fine point (2I+a, 2J+b) is (a+b) & 1: a red row sums its diagonal first, a black row last
+							const double t = stencil5_ord(1 + ((a + b) & 1), aS, aW, aC, aE, aN, ld<G>(x + o - P), ld<G>(x + o - 1), ld<G>(x + o), ld<G>(x + o + 1), ld<G>(x + o + P));
+							r[a * 3 + b] = sub(ld<G>(F.b + o), t);
+						} else {
+							const double t = stencil5(aS, aW, aC, aE, aN, ld<G>(x + o - P), ld<G>(x + o - 1), ld<G>(x + o), ld<G>(x + o + 1), ld<G>(x + o + P));
+							const double term = mul(Rw.w[a * 3 + b], sub(ld<G>(F.b + o), t));
+							sum = (a == 0 && b == 0) ? term : add(sum, term);
+						}
 					}
+				}
+				if (RB) {
+					// the five red fine points, then the four black ones
+					sum = mul(Rw.w[0], r[0]);
+					sum = add(sum, mul(Rw.w[2], r[2])); sum = add(sum, mul(Rw.w[4], r[4])); sum = add(sum, mul(Rw.w[6], r[6])); sum = add(sum, mul(Rw.w[8], r[8]));
+					sum = add(sum, mul(Rw.w[1], r[1])); sum = add(sum, mul(Rw.w[3], r[3])); sum = add(sum, mul(Rw.w[5], r[5])); sum = add(sum, mul(Rw.w[7], r[7]));
 				}
 				out = sum;
 			}
@@ -126,8 +169,8 @@ __device__ __forceinline__ void residual_restrict(const CLevel &F, const double 
 		}
 	}
 }
-// x += pro * xc   (k_prolong_add, natural numbering; one thread per fine point)
-template <int MULTADD, bool G>
+// x += pro * xc   (k_prolong_add; one thread per fine point; RB: the terms in ascending red-first coarse number)
+template <int MULTADD, bool G, bool RB>
 __device__ __forceinline__ void prolong_add(const CLevel &F, double *x, const CLevel &C, const double *xc, const Stencil3 &Pw, const Rows &R)
 {
 	const ptrdiff_t PC = C.pitch;
@@ -145,18 +188,24 @@ __device__ __forceinline__ void prolong_add(const CLevel &F, double *x, const CL
 						out = MULTADD ? add(u, s0) : add(u, mul(1.0, s0));
 					} else {
 						const double cm = mul(Pw.w[3 + 2], ld<G>(c + Jm)), c0 = mul(Pw.w[3 + 0], ld<G>(c + J0));
-						out = MULTADD ? add(add(u, cm), c0) : add(u, mul(1.0, add(cm, c0)));
+						const bool sw = RB && (((((i - 1) >> 1) + Jm) & 1) != 0);   // (I,Jm) black: the red (I,J0) comes first
+						const double t0 = sw ? c0 : cm, t1 = sw ? cm : c0;
+						out = MULTADD ? add(add(u, t0), t1) : add(u, mul(1.0, add(t0, t1)));
 					}
 				} else {
 					const double *cA = xc + (ptrdiff_t)((i >> 1) - 1) * PC;     // row -1: the zero ghost row
 					const double *cB = cA + PC;
+					const bool red_am = !RB || (((((i >> 1) - 1) + Jm) & 1) == 0);     // (IA,Jm) and (IB,J0) share a colour
 					if (j & 1) {
 						const double sa = mul(Pw.w[6 + 1], ld<G>(cA + J0)), sb = mul(Pw.w[0 + 1], ld<G>(cB + J0));
-						out = MULTADD ? add(add(u, sa), sb) : add(u, mul(1.0, add(sa, sb)));
+						const double s0 = (RB && red_am) ? sb : sa, s1 = (RB && red_am) ? sa : sb;   // (IA,J0) black, (IB,J0) red
+						out = MULTADD ? add(add(u, s0), s1) : add(u, mul(1.0, add(s0, s1)));
 					} else {
 						const double am = mul(Pw.w[6 + 2], ld<G>(cA + Jm)), a0 = mul(Pw.w[6 + 0], ld<G>(cA + J0));
 						const double bm = mul(Pw.w[0 + 2], ld<G>(cB + Jm)), b0 = mul(Pw.w[0 + 0], ld<G>(cB + J0));
-						out = MULTADD ? add(add(add(add(u, am), a0), bm), b0) : add(u, mul(1.0, add(add(add(am, a0), bm), b0)));
+						double t0 = am, t1 = a0, t2 = bm, t3 = b0;
+						if (RB) { if (red_am) { t0 = am; t1 = b0; t2 = a0; t3 = bm; } else { t0 = a0; t1 = bm; t2 = am; t3 = b0; } }
+						out = MULTADD ? add(add(add(add(u, t0), t1), t2), t3) : add(u, mul(1.0, add(add(add(t0, t1), t2), t3)));
 					}
 				}
 			}
@@ -166,12 +215,31 @@ __device__ __forceinline__ void prolong_add(const CLevel &F, double *x, const CL
 }
 }  // namespace ccy
 
+// One smoothing call on a level: Jacobi = first sweep from the zero guess (down) + out-of-place sweeps that swap x and w;
+// red-black SOR = in-place half sweeps in the colours of `mask`, the first one of a zero-guess call on an implied zero
+// iterate.  SYNC() separates the phases; *swapped toggles with every out-of-place sweep.
+template <bool G, bool RB, class SYNC>
+__device__ __forceinline__ void cc_smooth(const CoarseArgs &A, const CLevel &L, bool zero_guess, int its, unsigned mask, unsigned *swapped, int bit,
+                                          const ccy::Rows &R, SYNC sync)
+{
+	auto X = [&]() { return (*swapped >> bit) & 1u ? L.w : L.x; };
+	auto W = [&]() { return (*swapped >> bit) & 1u ? L.x : L.w; };
+	if (RB) {
+		const double om1 = sub(1.0, A.omega);
+		for (int k = 0; k < its; ++k) { ccy::rb_half<G>(L, X(), (int)((mask >> k) & 1u), om1, zero_guess && k == 0, R); sync(); }
+		return;
+	}
+	int k = 0;
+	if (zero_guess) { ccy::first_sweep<G>(L, X(), R); sync(); k = 1; }
+	for (; k < its; ++k) { ccy::sweep<G>(L, X(), W(), R); sync(); *swapped ^= 1u << bit; }
+}
+
 // the whole sub-cycle of levels lo .. nlev-1 inside ONE CTA with everything in shared memory (levels of at most
 // CC_TINY rows): __syncthreads between phases instead of cluster barriers and L2 round trips
 #define CC_TINY 31
 #define CC_TINY_DOUBLES 1792              // per vector, all tiny levels together (ghost row above and below each level)
 #define CC_TINY_COEF 512                  // coefficient rows of all tiny levels (8 doubles per grid row)
-template <int MULTADD>
+template <int MULTADD, bool RB>
 __device__ void tiny_cycle(const CoarseArgs &A, int lo, double *sx, double *sw, double *sb, double *sc, const ccy::Rows &R)
 {
 	CLevel T[6];
@@ -194,17 +262,15 @@ __device__ void tiny_cycle(const CoarseArgs &A, int lo, double *sx, double *sw, 
 	__syncthreads();
 	unsigned swapped = 0u;
 	auto X = [&](int l) { return (swapped >> l) & 1u ? T[l].w : T[l].x; };
-	auto W = [&](int l) { return (swapped >> l) & 1u ? T[l].x : T[l].w; };
+	auto bar = [&]() { __syncthreads(); };
 	for (int l = 0; l < nt; ++l) {
-		ccy::first_sweep<false>(T[l], X(l), R);
-		__syncthreads();
-		for (int k = 1; k < T[l].its_down; ++k) { ccy::sweep<false>(T[l], X(l), W(l), R); __syncthreads(); swapped ^= 1u << l; }
-		if (l + 1 < nt) { ccy::residual_restrict<false>(T[l], X(l), T[l + 1], A.R3, R); __syncthreads(); }
+		cc_smooth<false, RB>(A, T[l], true, T[l].its_down, T[l].mask_down, &swapped, l, R, bar);
+		if (l + 1 < nt) { ccy::residual_restrict<false, RB>(T[l], X(l), T[l + 1], A.R3, R); __syncthreads(); }
 	}
 	for (int l = nt - 2; l >= 0; --l) {
-		ccy::prolong_add<MULTADD, false>(T[l], X(l), T[l + 1], X(l + 1), A.P3, R);
+		ccy::prolong_add<MULTADD, false, RB>(T[l], X(l), T[l + 1], X(l + 1), A.P3, R);
 		__syncthreads();
-		for (int k = 0; k < T[l].its_up; ++k) { ccy::sweep<false>(T[l], X(l), W(l), R); __syncthreads(); swapped ^= 1u << l; }
+		cc_smooth<false, RB>(A, T[l], false, T[l].its_up, T[l].mask_up, &swapped, l, R, bar);
 	}
 	// the correction of the first tiny level goes back to global memory, into the buffer the host expects after the
 	// same number of swaps; the deeper levels' vectors are scratch and need not be written back
@@ -213,12 +279,11 @@ __device__ void tiny_cycle(const CoarseArgs &A, int lo, double *sx, double *sw, 
 	for (int k = threadIdx.x; k < T[0].ni * T[0].pitch; k += blockDim.x) gx[k] = sxf[k];
 }
 
-__global__ void __cluster_dims__(CC_CTAS, 1, 1) __launch_bounds__(CC_THREADS)
-k_coarse_cycle(CoarseArgs A)
+template <bool RB>
+__device__ __forceinline__ void coarse_cycle_body(const CoarseArgs &A, double *sx, double *sw, double *sb, double *sc)
 {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster();
-	__shared__ double sx[CC_TINY_DOUBLES], sw[CC_TINY_DOUBLES], sb[CC_TINY_DOUBLES], sc[CC_TINY_COEF];
 	ccy::Rows R;
 	R.lane = threadIdx.x & 31;
 	R.gw = (int)cluster.block_rank() * (CC_THREADS / 32) + (threadIdx.x >> 5);
@@ -240,30 +305,24 @@ k_coarse_cycle(CoarseArgs A)
 	// has its iterate in lev[l].w (the host applies the same number of swaps to its own pointers after the launch)
 	unsigned swapped = 0u;
 	auto X = [&](int l) { return (swapped >> l) & 1u ? A.lev[l].w : A.lev[l].x; };
-	auto W = [&](int l) { return (swapped >> l) & 1u ? A.lev[l].x : A.lev[l].w; };
+	auto bar = [&]() { cluster.sync(); };
 	// ---- down (levels 0 .. lt-1 by the whole cluster)
 	for (int l = 0; l < lt; ++l) {
 		const CLevel &L = A.lev[l];
-		ccy::first_sweep<true>(L, X(l), R);
-		cluster.sync();
-		for (int k = 1; k < L.its_down; ++k) {
-			ccy::sweep<true>(L, X(l), W(l), R);
-			cluster.sync();
-			swapped ^= 1u << l;
-		}
+		cc_smooth<true, RB>(A, L, true, L.its_down, L.mask_down, &swapped, l, R, bar);
 		if (l + 1 < A.nlev) {
-			ccy::residual_restrict<true>(L, X(l), A.lev[l + 1], A.R3, R);
+			ccy::residual_restrict<true, RB>(L, X(l), A.lev[l + 1], A.R3, R);
 			cluster.sync();
 		}
 	}
 	// ---- the tiny tail in one CTA's shared memory
 	if (lt < A.nlev) {
 		if (cluster.block_rank() == 0) {
-			if (A.multadd) tiny_cycle<1>(A, lt, sx, sw, sb, sc, R1);
-			else           tiny_cycle<0>(A, lt, sx, sw, sb, sc, R1);
+			if (A.multadd) tiny_cycle<1, RB>(A, lt, sx, sw, sb, sc, R1);
+			else           tiny_cycle<0, RB>(A, lt, sx, sw, sb, sc, R1);
 		}
 		// host-side bookkeeping counts the swaps of every level; the first tiny level's result was stored accordingly
-		{
+		if (!RB) {
 			const CLevel &L = A.lev[lt];
 			const int sw_count = (lt == A.nlev - 1) ? L.its_down - 1 : (L.its_down - 1) + L.its_up;
 			if (sw_count & 1) swapped ^= 1u << lt;
@@ -274,13 +333,18 @@ k_coarse_cycle(CoarseArgs A)
 	for (int l = lt - 1; l >= 0; --l) {
 		if (l + 1 >= A.nlev) continue;
 		const CLevel &L = A.lev[l];
-		if (A.multadd) ccy::prolong_add<1, true>(L, X(l), A.lev[l + 1], X(l + 1), A.P3, R);
-		else           ccy::prolong_add<0, true>(L, X(l), A.lev[l + 1], X(l + 1), A.P3, R);
+		if (A.multadd) ccy::prolong_add<1, true, RB>(L, X(l), A.lev[l + 1], X(l + 1), A.P3, R);
+		else           ccy::prolong_add<0, true, RB>(L, X(l), A.lev[l + 1], X(l + 1), A.P3, R);
 		cluster.sync();
-		for (int k = 0; k < L.its_up; ++k) {
-			ccy::sweep<true>(L, X(l), W(l), R);
-			cluster.sync();
-			swapped ^= 1u << l;
-		}
+		cc_smooth<true, RB>(A, L, false, L.its_up, L.mask_up, &swapped, l, R, bar);
 	}
+}
+
+__global__ void __cluster_dims__(CC_CTAS, 1, 1) __launch_bounds__(CC_THREADS)
+k_coarse_cycle(CoarseArgs A)
+{
+	pdl_enter();
+	__shared__ double sx[CC_TINY_DOUBLES], sw[CC_TINY_DOUBLES], sb[CC_TINY_DOUBLES], sc[CC_TINY_COEF];
+	if (A.rb) coarse_cycle_body<true>(A, sx, sw, sb, sc);
+	else      coarse_cycle_body<false>(A, sx, sw, sb, sc);
 }

@@ -42,6 +42,15 @@ __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, 
 // the sum gives the same bits as the reference's separate multiply and add
 __device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream is still draining; it must not touch memory before pdl_wait() (which
+// returns once the predecessor grid has completed and its writes are visible -- a no-op in an ordinary launch).
+// pdl_go() lets the successor's blocks be scheduled as soon as every block of this grid has started: launch latency
+// and block start-up of the ~26 dependent launches of a V-cycle overlap the tail of the previous kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_go() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_go(); }
+
 // (A x)_ij in MatMult_SeqAIJ order: ascending columns row-n, row-1, row, row+1, row+n
 // (ref call sites: src/solver.c:1516,1534,1545; the ghost zeros stand in for the entries fillJacobians drops)
 __device__ __forceinline__ double stencil5(double aS, double aW, double aC, double aE, double aN,

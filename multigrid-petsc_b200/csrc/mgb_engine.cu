@@ -53,6 +53,24 @@ static int fail(int code, const char *fmt, ...)
 #define KCHECK() CU(cudaGetLastError())
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Launch with programmatic stream serialisation (PDL): the kernel may become resident while its predecessor drains; every
+// kernel launched through here starts with pdl_enter() (mgb_common.cuh).  Inside a stream capture the launch becomes a
+// programmatic edge of the graph.  Off by default: measured on B200 (gpurun_out/r2q_*), the replayed cycle graph gains
+// nothing at 1025^2 and above (the legs are bound by their own row pipeline, not by the launch gap) and 4-15 % only on
+// 129^2-sized problems; MGB_PDL=1 turns it on.  A launch error is left for KCHECK().
+static bool g_pdl = false;
+template <class... KP, class... A>
+static void klaunch(void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A &&...args)
+{
+	cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+	(void)cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ engine state
 #define MGB_MAXL 32
 #define NOOFF ((size_t)-1)
@@ -361,6 +379,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	CU(cudaStreamSynchronize(e->strips[0].stream));
 	e->connected = (P == 1) || nlocal > 1;
 	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
+	{ const char *v = getenv("MGB_PDL"); if (v && v[0]) g_pdl = v[0] != '0'; }
 	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }
@@ -912,7 +931,7 @@ static int vec_zero(mgb_engine *e, int which, int level)
 		if (!S.present || !S.active) continue;
 		const size_t n2 = (size_t)(S.ni + 2 * MGB_GHOST_ROWS) * g.pitch / 2;
 		const int blocks = (int)((n2 + 255) / 256 < 2368 ? (n2 + 255) / 256 : 2368);
-		k_axpy<3><<<blocks, 256, 0, s.stream>>>(S.v[which] - (size_t)MGB_GHOST_ROWS * g.pitch, nullptr, n2, 0.0, nullptr, 0.0);
+		klaunch(k_axpy<3>, dim3(blocks), dim3(256), 0, s.stream, S.v[which] - (size_t)MGB_GHOST_ROWS * g.pitch, nullptr, n2, 0.0, nullptr, 0.0);
 		LAUNCHED(e); KCHECK();
 	}
 	return MGB_OK;
@@ -966,7 +985,7 @@ static int k_apply(mgb_engine *e, int l, int xv, int yv)
 		if (!computes(s, l)) continue;
 		SLevel &S = s.lev[l];
 		const int ry = pick_ry(g, S.ni);
-		k_stream5<ST_APPLY><<<stream_grid(g, S.ni, ry), MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], nullptr, S.v[yv], ldev(e, s, l), 0.0, nullptr, ry);
+		klaunch(k_stream5<ST_APPLY>, dim3(stream_grid(g, S.ni, ry)), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], nullptr, S.v[yv], ldev(e, s, l), 0.0, nullptr, ry);
 		LAUNCHED(e); KCHECK();
 	}
 	return MGB_OK;
@@ -979,7 +998,7 @@ static int k_residual(mgb_engine *e, int l, int xv, int bv, int rv)
 		if (!computes(s, l)) continue;
 		SLevel &S = s.lev[l];
 		const int ry = pick_ry(g, S.ni);
-		k_stream5<ST_RESID><<<stream_grid(g, S.ni, ry), MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], S.v[rv], ldev(e, s, l), 0.0, nullptr, ry);
+		klaunch(k_stream5<ST_RESID>, dim3(stream_grid(g, S.ni, ry)), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], S.v[bv], S.v[rv], ldev(e, s, l), 0.0, nullptr, ry);
 		LAUNCHED(e); KCHECK();
 	}
 	return MGB_OK;
@@ -1008,14 +1027,14 @@ static int reduce_tail(mgb_engine *e, int l, const std::vector<int> &nblocks, in
 			a.status = status_of(e, s); a.status_host = s.status_host_dev; a.spin_limit = e->spin_limit;
 			if (e->strips.size() > 1) a.do_wait = 0;               // emulation: every strip pushes first ...
 		}
-		k_reduce_tail<<<1, 1024, 0, s.stream>>>(a);
+		klaunch(k_reduce_tail, dim3(1), dim3(1024), 0, s.stream, a);
 		LAUNCHED(e); KCHECK();
 		args.push_back(a);
 	}
 	if (global && e->strips.size() > 1)
 		for (size_t k = 0; k < args.size(); ++k) {                 // ... then every strip waits and sums
 			TailArgs a = args[k]; a.do_push = 0; a.do_wait = 1;
-			k_reduce_tail<<<1, 32, 0, e->strips[k].stream>>>(a);
+			klaunch(k_reduce_tail, dim3(1), dim3(32), 0, e->strips[k].stream, a);
 			LAUNCHED(e); KCHECK();
 		}
 	return MGB_OK;
@@ -1032,7 +1051,7 @@ static int k_resnorm(mgb_engine *e, int l, int xv, int bv, int slot)
 		const int ry = pick_ry(g, S.ni);
 		const dim3 gr = stream_grid(g, S.ni, ry);
 		if ((size_t)gr.x * gr.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
-		k_stream5<ST_RESNORM><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], nullptr, ldev(e, s, l), 0.0, s.partial, ry);
+		klaunch(k_stream5<ST_RESNORM>, dim3(gr), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], S.v[bv], nullptr, ldev(e, s, l), 0.0, s.partial, ry);
 		LAUNCHED(e); KCHECK();
 		nb.push_back((int)(gr.x * gr.y));
 	}
@@ -1049,8 +1068,8 @@ static int k_reduce(mgb_engine *e, int l, int xv, int yv, int slot, int take_sqr
 		const size_t n2 = (size_t)S.ni * g.pitch / 2;
 		size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
 		const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
-		if (yv >= 0) k_reduce1<1><<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], S.v[yv], n2, s.partial);
-		else         k_reduce1<0><<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], nullptr, n2, s.partial);
+		if (yv >= 0) klaunch(k_reduce1<1>, dim3(blocks), dim3(MGB_RED_THREADS), 0, s.stream, S.v[xv], S.v[yv], n2, s.partial);
+		else         klaunch(k_reduce1<0>, dim3(blocks), dim3(MGB_RED_THREADS), 0, s.stream, S.v[xv], nullptr, n2, s.partial);
 		LAUNCHED(e); KCHECK();
 		nb.push_back(blocks);
 	}
@@ -1066,7 +1085,7 @@ static int k_vecop(mgb_engine *e, int l, int yv, int xv, double alpha, int alpha
 		const size_t n2 = (size_t)S.ni * g.pitch / 2;
 		size_t want = (n2 + 255) / 256;
 		const int blocks = (int)(want < 1 ? 1 : (want > 148 * 32 ? 148 * 32 : want));
-		k_axpy<KIND><<<blocks, 256, 0, s.stream>>>(S.v[yv], S.v[xv], n2, alpha, alpha_slot >= 0 ? s.scal + alpha_slot : nullptr, 1.0);
+		klaunch(k_axpy<KIND>, dim3(blocks), dim3(256), 0, s.stream, S.v[yv], S.v[xv], n2, alpha, alpha_slot >= 0 ? s.scal + alpha_slot : nullptr, 1.0);
 		LAUNCHED(e); KCHECK();
 	}
 	return MGB_OK;
@@ -1083,7 +1102,7 @@ static int k_apply_dot(mgb_engine *e, int l, int xv, int yv, int slot, int post_
 		const int ry = pick_ry(g, S.ni);
 		const dim3 gr = stream_grid(g, S.ni, ry);
 		if ((size_t)gr.x * gr.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
-		k_stream5<ST_APPLYDOT><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], nullptr, S.v[yv], ldev(e, s, l), 0.0, s.partial, ry);
+		klaunch(k_stream5<ST_APPLYDOT>, dim3(gr), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], nullptr, S.v[yv], ldev(e, s, l), 0.0, s.partial, ry);
 		LAUNCHED(e); KCHECK();
 		nb.push_back((int)(gr.x * gr.y));
 	}
@@ -1100,7 +1119,7 @@ static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, doubl
 		const size_t n2 = (size_t)S.ni * g.pitch / 2;
 		size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
 		const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
-		k_cg_update<<<blocks, MGB_RED_THREADS, 0, s.stream>>>(S.v[xv], S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial, a_slot >= 0 ? s.scal + a_slot : nullptr);
+		klaunch(k_cg_update, dim3(blocks), dim3(MGB_RED_THREADS), 0, s.stream, S.v[xv], S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial, a_slot >= 0 ? s.scal + a_slot : nullptr);
 		LAUNCHED(e); KCHECK();
 		nb.push_back(blocks);
 	}
@@ -1129,8 +1148,8 @@ static int k_rb(mgb_engine *e, int l, int xv, int bv, int colour, double omega, 
 		SLevel &S = s.lev[l];
 		const int ry = pick_ry(g, S.ni);
 		const dim3 gr = stream_grid(g, S.ni, ry);
-		if (variant == 0) k_rb_half<0><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], ldev(e, s, l), colour, omega, ry);
-		else              k_rb_half<1><<<gr, MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], ldev(e, s, l), colour, omega, ry);
+		if (variant == 0) klaunch(k_rb_half<0>, dim3(gr), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], S.v[bv], ldev(e, s, l), colour, omega, ry);
+		else              klaunch(k_rb_half<1>, dim3(gr), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], S.v[bv], ldev(e, s, l), colour, omega, ry);
 		LAUNCHED(e); KCHECK();
 	}
 	return halo(e, l, xv, 2);
@@ -1190,7 +1209,7 @@ static int smooth(mgb_engine *e, int l, const mgb_smoother *sm, int its, bool gu
 				if (!computes(s, l)) continue;
 				SLevel &S = s.lev[l];
 				dim3 gr(cdiv(g.pitch, 512), S.ni);
-				k_jacobi_first<<<gr, 256, 0, s.stream>>>(S.v[bv], S.v[xv], ldev(e, s, l), sm->scale);
+				klaunch(k_jacobi_first, dim3(gr), dim3(256), 0, s.stream, S.v[bv], S.v[xv], ldev(e, s, l), sm->scale);
 				LAUNCHED(e); KCHECK();
 			}
 			TRY(halo(e, l, xv, 2));
@@ -1202,7 +1221,7 @@ static int smooth(mgb_engine *e, int l, const mgb_smoother *sm, int its, bool gu
 				if (!computes(s, l)) continue;
 				SLevel &S = s.lev[l];
 				const int ry = pick_ry(g, S.ni);
-				k_stream5<ST_JACOBI><<<stream_grid(g, S.ni, ry), MGB_SB_THREADS, 0, s.stream>>>(S.v[xv], S.v[bv], S.v[sv], ldev(e, s, l), sm->scale, nullptr, ry);
+				klaunch(k_stream5<ST_JACOBI>, dim3(stream_grid(g, S.ni, ry)), dim3(MGB_SB_THREADS), 0, s.stream, S.v[xv], S.v[bv], S.v[sv], ldev(e, s, l), sm->scale, nullptr, ry);
 				LAUNCHED(e); KCHECK();
 			}
 			swap_vec(e, l, xv, sv);
@@ -1331,8 +1350,8 @@ static int restrict_to_coarse(mgb_engine *e, int l, int bv, int xv, int rv, bool
 		size_t coff; const LevelDev cd = coarse_view(e, s, l + 1, gf.dist, &coff);
 		dim3 blk(32, 4), gr(cdiv(gc.pitch, 32), cdiv(cd.ni, 4));
 		double *bc = C.v[MGB_VEC_B] + coff;
-		if (fused) k_restrict<1><<<gr, blk, 0, s.stream>>>(F.v[xv], F.v[bv], nullptr, bc, ldev(e, s, l), cd, e->R3);
-		else       k_restrict<0><<<gr, blk, 0, s.stream>>>(nullptr, nullptr, F.v[rv], bc, ldev(e, s, l), cd, e->R3);
+		if (fused) klaunch(k_restrict<1>, dim3(gr), dim3(blk), 0, s.stream, F.v[xv], F.v[bv], nullptr, bc, ldev(e, s, l), cd, e->R3);
+		else       klaunch(k_restrict<0>, dim3(gr), dim3(blk), 0, s.stream, nullptr, nullptr, F.v[rv], bc, ldev(e, s, l), cd, e->R3);
 		LAUNCHED(e); KCHECK();
 	}
 	if (gc.dist) return halo(e, l + 1, MGB_VEC_B, 2);
@@ -1351,8 +1370,8 @@ static int prolong_add(mgb_engine *e, int l, int xv, bool multadd)
 		size_t coff; const LevelDev cd = coarse_view(e, s, l + 1, gf.dist, &coff);
 		dim3 blk(32, 4), gr(cdiv(gf.pitch, 64), cdiv(F.ni, 4));
 		const double *uc = C.v[MGB_VEC_U] + coff;
-		if (multadd) k_prolong_add<1><<<gr, blk, 0, s.stream>>>(F.v[xv], uc, ldev(e, s, l), cd, e->P3);
-		else         k_prolong_add<0><<<gr, blk, 0, s.stream>>>(F.v[xv], uc, ldev(e, s, l), cd, e->P3);
+		if (multadd) klaunch(k_prolong_add<1>, dim3(gr), dim3(blk), 0, s.stream, F.v[xv], uc, ldev(e, s, l), cd, e->P3);
+		else         klaunch(k_prolong_add<0>, dim3(gr), dim3(blk), 0, s.stream, F.v[xv], uc, ldev(e, s, l), cd, e->P3);
 		LAUNCHED(e); KCHECK();
 	}
 	return halo(e, l, xv, 2);
@@ -1386,7 +1405,7 @@ static void launch_jfused(const FusedArgs &a, dim3 grid, cudaStream_t st)
 				optin[dev] = true;                 // on failure the launch below reports the error through KCHECK
 		}
 	}
-	k_jfused<D, PRE, POST, SMK><<<grid, FJ_THREADS, jf_smem_bytes<D>(), st>>>(a);
+	klaunch(k_jfused<D, PRE, POST, SMK>, dim3(grid), dim3(FJ_THREADS), jf_smem_bytes<D>(), st, a);
 }
 
 template <int D, int SMK = 0>
@@ -1624,7 +1643,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 		for (auto &s : e->strips) {
 			if (!computes(s, l)) {
 				// the ranks that do not compute on a broadcast level keep their version counter of the channel in step
-				if (bcast_k) { k_bump<<<1, 1, 0, s.stream>>>(ver_of(e, s) + CH_BCAST(l)); LAUNCHED(e); KCHECK(); }
+				if (bcast_k) { klaunch(k_bump, dim3(1), dim3(1), 0, s.stream, ver_of(e, s) + CH_BCAST(l)); LAUNCHED(e); KCHECK(); }
 				continue;
 			}
 			SLevel &S = s.lev[l];
@@ -1693,29 +1712,42 @@ static int bottom_start(const mgb_engine *e)
 }
 // levels lp .. L-1 in one launch on rank 0: zero-guess smoothing and restriction down, the coarsest smoothing,
 // correction and smoothing up.  b[lp] must be complete on rank 0; on return u[lp] holds the correction.
-static int bottom_cycle(mgb_engine *e, int lp, int its_level, double scale_level, int its_coarse, double scale_coarse, bool multadd)
+static int bottom_cycle(mgb_engine *e, int lp, const mgb_smoother *sm_level, int its_level, const mgb_smoother *sm_coarse, int its_coarse, bool multadd)
 {
 	TRY(flush_levels(e, lp, MGB_MAXL));
+	const bool rb = sm_level->type == MGB_SMOOTH_RBSOR;
+	// red-black SOR: the half sweeps of one smoothing call (colours in launch order), at most 32 per call
+	const std::vector<int> st_level = smoother_stages(sm_level, its_level), st_coarse = smoother_stages(sm_coarse, its_coarse);
+	if (rb && (st_level.size() > 32 || st_coarse.size() > 32)) return fail(MGB_EINVAL, "too many half sweeps per smoothing call for the bottom kernel");
+	auto mask_of = [](const std::vector<int> &st) { unsigned m = 0u; for (size_t k = 0; k < st.size(); ++k) if (st[k] == 1) m |= 1u << k; return m; };
 	for (auto &s : e->strips) {
 		if (s.rank != 0) continue;
 		CoarseArgs a; memset(&a, 0, sizeof a);
 		a.nlev = e->L - lp; a.multadd = multadd ? 1 : 0; a.R3 = e->R3; a.P3 = e->P3;
+		a.rb = rb ? 1 : 0; a.omega = sm_level->omega;
 		for (int l = lp; l < e->L; ++l) {
 			SLevel &S = s.lev[l]; CLevel &c = a.lev[l - lp];
 			const bool last = l == e->L - 1;
 			c.x = S.v[MGB_VEC_U]; c.w = S.v[MGB_VEC_W]; c.b = S.v[MGB_VEC_B]; c.coef = S.coef;
 			c.ni = S.ni; c.nj = e->geo[l].nj; c.pitch = e->geo[l].pitch; c.uniform = e->geo[l].uniform;
-			c.its_down = last ? its_coarse : its_level; c.its_up = last ? 0 : its_level;
-			c.scale = last ? scale_coarse : scale_level;
+			if (rb) {
+				c.its_down = (int)(last ? st_coarse.size() : st_level.size()); c.its_up = last ? 0 : (int)st_level.size();
+				c.mask_down = last ? mask_of(st_coarse) : mask_of(st_level); c.mask_up = last ? 0u : mask_of(st_level);
+				c.scale = 1.0;
+			} else {
+				c.its_down = last ? its_coarse : its_level; c.its_up = last ? 0 : its_level;
+				c.scale = last ? sm_coarse->scale : sm_level->scale;
+			}
 		}
-		k_coarse_cycle<<<CC_CTAS, CC_THREADS, 0, s.stream>>>(a);
+		klaunch(k_coarse_cycle, dim3(CC_CTAS), dim3(CC_THREADS), 0, s.stream, a);
 		LAUNCHED(e); KCHECK();
 	}
-	for (int l = lp; l < e->L; ++l) {
-		const bool last = l == e->L - 1;
-		const int swaps = last ? its_coarse - 1 : (its_level - 1) + its_level;
-		if (swaps & 1) swap_vec(e, l, MGB_VEC_U, MGB_VEC_W);
-	}
+	if (!rb)                                                  // red-black half sweeps are in place: no ping-pong
+		for (int l = lp; l < e->L; ++l) {
+			const bool last = l == e->L - 1;
+			const int swaps = last ? its_coarse - 1 : (its_level - 1) + its_level;
+			if (swaps & 1) swap_vec(e, l, MGB_VEC_U, MGB_VEC_W);
+		}
 	return MGB_OK;
 }
 
@@ -1874,8 +1906,8 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 		if (Lc == 1) {
 			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_NORM, B, U, W, 0));
 		} else {
-			// levels lp .. Lc-1: one persistent launch (Jacobi only)
-			const int lp = (p->no_bottom || s->type != MGB_SMOOTH_JACOBI) ? Lc : bottom_start(e);
+			// levels lp .. Lc-1: one persistent launch (Jacobi, or red-black SOR in the fusable sweep orders)
+			const int lp = p->no_bottom ? Lc : bottom_start(e);
 			for (int l = 0; l < Lc - 1 && l < lp; ++l) {                                                    // :1531-1536
 				const bool zero = l > 0 || first;
 				if (FL(l)) TRY(fused_leg(e, l, s, p->v0, zero ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));
@@ -1887,7 +1919,7 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 			}
 			if (lp < Lc) {
 				if (lp == e->La && ik) TRY(wait_gather(e, lp));        // the bottom kernel consumes the gathered right-hand side
-				TRY(bottom_cycle(e, lp, p->v0, s->scale, p->v1, s->scale, false));
+				TRY(bottom_cycle(e, lp, s, p->v0, s, p->v1, false));
 			} else if (FL(Lc - 1)) TRY(fused_leg(e, Lc - 1, s, p->v1, PRE_ZERO, POST_NONE, B, U, W, 0, true));    // :1536 coarsest
 			else {
 				if (ik && Lc - 1 == e->La) TRY(wait_gather(e, Lc - 1));
@@ -2113,10 +2145,10 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 	// (bottom kernel, LU, one-sweep kernels) gets a wait launch on rank 0 (harmless when a fused leg follows)
 	if (e->P > 1 && e->inkernel && l == e->La && l >= 1) TRY(wait_gather(e, l));
 	if (l >= 1 && !p->no_fuse && !p->no_bottom && p->coarse == MGB_COARSE_RICHARDSON && fusable(e, &p->level_smoother) &&
-	    fusable(e, &p->coarse_smoother) && p->level_smoother.type == MGB_SMOOTH_JACOBI && p->coarse_smoother.type == MGB_SMOOTH_JACOBI &&
+	    fusable(e, &p->coarse_smoother) && p->level_smoother.type == p->coarse_smoother.type &&
 	    p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e) &&
 	    bv == MGB_VEC_B && xv == MGB_VEC_U)
-		return bottom_cycle(e, l, p->level_its, p->level_smoother.scale, p->coarse_its, p->coarse_smoother.scale, true);
+		return bottom_cycle(e, l, &p->level_smoother, p->level_its, &p->coarse_smoother, p->coarse_its, true);
 	if (l == Lc - 1) {
 		if (p->coarse == MGB_COARSE_RICHARDSON) {
 			if (!p->no_fuse && fusable(e, &p->coarse_smoother) && fuse_level(e, &p->coarse_smoother, l) && p->coarse_its >= 1)
@@ -2211,7 +2243,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 		reason = ksp_converged(p, 0, dp, &rnorm0, &ttol);
 		if (!reason) {
 			TRY(vec_zero(e, Pv, 0));                                                               // p = 0: the first p = z + 0 p
-			for (auto &s : e->strips) { k_set_scalar<<<1, 1, 0, s.stream>>>(s.scal + SC_BETA, INFINITY); LAUNCHED(e); KCHECK(); }
+			for (auto &s : e->strips) { klaunch(k_set_scalar, dim3(1), dim3(1), 0, s.stream, s.scal + SC_BETA, INFINITY); LAUNCHED(e); KCHECK(); }
 			auto iteration = [&]() -> int {
 				bool dot_done = false;
 				TRY(halo(e, 0, R, HALO_DEPTH));
@@ -2319,7 +2351,7 @@ extern "C" int mgb_time_op(mgb_engine *e, int op, int level, int reps, double *m
 			case 17: TRY(halo(e, level, U, HALO_DEPTH)); TRY(flush_all(e)); break;
 			case 18: TRY(k_reduce(e, level, U, -1, 0, 1)); break;
 			case 16: if (level < 1) return fail(MGB_EINVAL, "the bottom kernel starts at level >= 1");
-			         TRY(bottom_cycle(e, level, 3, 0.8, 3, 0.8, false)); break;
+			         TRY(bottom_cycle(e, level, &jac, 3, &jac, 3, false)); break;
 			default: return fail(MGB_EINVAL, "unknown op %d", op);
 			}
 			TRY(flush_all(e));               // transfers requested by the operation belong to its cost

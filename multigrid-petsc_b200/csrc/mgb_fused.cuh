@@ -606,6 +606,7 @@ k_jfused(FusedArgs A)
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
+	pdl_enter();                                          // nothing above touches global memory (programmatic dependent launch)
 	B.tid = threadIdx.x;
 	B.c0 = blockIdx.x * FJ_VALID;                         // first valid column of the tile
 	B.j0 = B.c0 - FJ_HALO + 2 * B.tid;                    // this thread's columns j0, j0+1 (j0 even)

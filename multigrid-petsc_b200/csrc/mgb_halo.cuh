@@ -154,6 +154,7 @@ __device__ __forceinline__ void tail_finish(const TailArgs &a, double v)
 __global__ void __launch_bounds__(1024)
 k_reduce_tail(TailArgs a)
 {
+	pdl_enter();
 	double s = 0.0;
 	if (a.do_push) {
 		double acc = 0.0;
@@ -194,10 +195,10 @@ k_reduce_tail(TailArgs a)
 	}
 }
 
-__global__ void k_set_scalar(double *p, double v) { *p = v; }
+__global__ void k_set_scalar(double *p, double v) { pdl_enter(); *p = v; }
 
 // keeps a channel's version counter in step on a rank that takes no part in a transfer done inside a compute kernel
-__global__ void k_bump(unsigned long long *ver) { *ver = *ver + 1ull; }
+__global__ void k_bump(unsigned long long *ver) { pdl_enter(); *ver = *ver + 1ull; }
 
 // out[out_slot + k] = f(sum over ranks of slot[r][k]) in rank order (identical on every rank): the all-reduce tail.
 // slots: two parity sets of MGB_MAX_RANKS x 4 doubles (the set of the version just completed is read, so a fast

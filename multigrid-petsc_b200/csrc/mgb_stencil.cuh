@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(MGB_SB_THREADS)
 k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
           LevelDev L, double scale, double *__restrict__ partial, int ry)
 {
+	pdl_enter();
 	const int j0 = (blockIdx.x * MGB_SB_THREADS + threadIdx.x) * 2;
 	const int ibeg = blockIdx.y * ry;
 	const int iend = min(ibeg + ry, L.ni);
@@ -76,11 +77,71 @@ k_stream5(const double *__restrict__ x, const double *__restrict__ b, double *__
 	}
 }
 
+// CG direction step in one pass (KSPSolve_CG: VecAYPX(p, b, z) ; MatMult(A, p, w) ; VecDot(p, w), plus the VecAXPY(x, a, p) of
+// the PREVIOUS iteration, deferred to here because this pass reads the old p anyway):
+//     x += a_prev * p_old ;  p_new = z + b * p_old ;  w = A p_new ;  partial[block] = sum p_new . w
+// p_new is written OUT OF PLACE (pn: a block recomputes the rows above and below its chunk from z and p_old, which must not
+// have been overwritten by its neighbour) and, on a strip, also into the two ghost rows next to the strip: every rank derives
+// them from the ghost rows of z and p_old with the same arithmetic as their owner, so p needs no exchange of its own.
+// b = *ratio (beta / betaold) and a_prev = *alpha are device scalars left by the reduction tails.  48 B per unknown for
+// what took 24 (AYPX) + 16 (apply) + 24 (x += a p) as separate passes; per value the same operations in the same order.
+__global__ void __launch_bounds__(MGB_SB_THREADS)
+k_cg_pstep(const double *__restrict__ z, const double *__restrict__ p, double *__restrict__ pn, double *__restrict__ w,
+           double *__restrict__ x, LevelDev L, const double *__restrict__ ratio, const double *__restrict__ alpha,
+           double *__restrict__ partial, int ry)
+{
+	pdl_enter();
+	const int j0 = (blockIdx.x * MGB_SB_THREADS + threadIdx.x) * 2;
+	const int ibeg = blockIdx.y * ry;
+	const int iend = min(ibeg + ry, L.ni);
+	double acc = 0.0;
+	if (j0 < L.pitch) {
+		const double b = *ratio, a = *alpha;
+		const ptrdiff_t P = (ptrdiff_t)L.pitch;
+		ptrdiff_t o = (ptrdiff_t)ibeg * P + j0;
+		auto pn1 = [&](ptrdiff_t q) { return add(z[q], mul(b, p[q])); };
+		auto pn2 = [&](double2 zz, double2 pp) { return make_double2(add(zz.x, mul(b, pp.x)), add(zz.y, mul(b, pp.y))); };
+		const double *cf = L.coef + (size_t)(L.i0 + ibeg) * MGB_COEF_STRIDE;
+		double aS = cf[0], aW = cf[1], aC = cf[2], aE = cf[3], aN = cf[4];
+		double2 pm = pn2(ld2(z + o - P), ld2(p + o - P));          // row ibeg - 1
+		double2 poc = ld2(p + o);
+		double2 pc = pn2(ld2(z + o), poc);
+		double pw = pn1(o - 1), pe = pn1(o + 2);
+		const bool in0 = j0 < L.nj, in1 = j0 + 1 < L.nj;
+		if (ibeg == 0 && L.i0 > 0) st2(pn + o - P, pm);            // ghost row above the strip
+#pragma unroll 2
+		for (int i = ibeg; i < iend; ++i) {
+			const double2 pon = ld2(p + o + P);
+			const double2 pnx = pn2(ld2(z + o + P), pon);
+			const double pnw = pn1(o + P - 1), pne = pn1(o + P + 2);
+			if (!L.uniform) { aS = cf[0]; aW = cf[1]; aC = cf[2]; aE = cf[3]; aN = cf[4]; cf += MGB_COEF_STRIDE; }
+			const int rowpar = (L.i0 + i) & 1;
+			const int o0 = L.rb ? 1 + rowpar : 0, o1 = L.rb ? 2 - rowpar : 0;
+			double2 out;
+			out.x = stencil5_ord(o0, aS, aW, aC, aE, aN, pm.x, pw, pc.x, pc.y, pnx.x);
+			out.y = stencil5_ord(o1, aS, aW, aC, aE, aN, pm.y, pc.x, pc.y, pe, pnx.y);
+			if (!in0) out.x = 0.0;
+			if (!in1) out.y = 0.0;
+			st2(w + o, out);
+			st2(pn + o, pc);
+			acc += pc.x * out.x + pc.y * out.y;
+			double2 xv = ld2(x + o);
+			xv.x = add(xv.x, mul(a, poc.x)); xv.y = add(xv.y, mul(a, poc.y));
+			st2(x + o, xv);
+			pm = pc; pc = pnx; pw = pnw; pe = pne; poc = pon; o += P;
+		}
+		if (iend == L.ni && L.i0 + L.ni < L.gni) st2(pn + o, pc);  // ghost row below the strip (pc is row ni now)
+	}
+	const double s = block_sum<MGB_SB_THREADS>(acc);
+	if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
 // First Richardson iteration from a zero initial guess: r = b, z = r * dinv, x = 0 + scale * z
 // (KSPSolve_Richardson with guess_zero: no MatMult; ref: src/solver.c:1531-1532,1536).  16 B / unknown.
 __global__ void __launch_bounds__(256)
 k_jacobi_first(const double *__restrict__ b, double *__restrict__ x, LevelDev L, double scale)
 {
+	pdl_enter();
 	const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
 	const int i = blockIdx.y;
 	if (j0 >= L.pitch) return;
@@ -105,6 +166,7 @@ template <int VARIANT>
 __global__ void __launch_bounds__(MGB_SB_THREADS)
 k_rb_half(double *__restrict__ x, const double *__restrict__ b, LevelDev L, int colour, double omega, int ry)
 {
+	pdl_enter();
 	const int j0 = (blockIdx.x * MGB_SB_THREADS + threadIdx.x) * 2;
 	const int ibeg = blockIdx.y * ry;
 	const int iend = min(ibeg + ry, L.ni);

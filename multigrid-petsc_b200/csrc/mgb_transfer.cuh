@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128)
 k_restrict(const double *__restrict__ uf, const double *__restrict__ bf, const double *__restrict__ rf,
            double *__restrict__ bc, LevelDev F, LevelDev C, Stencil3 R)
 {
+	pdl_enter();
 	const int J = blockIdx.x * blockDim.x + threadIdx.x;
 	const int I = blockIdx.y * blockDim.y + threadIdx.y;
 	if (I >= C.ni || J >= C.pitch) return;
@@ -76,6 +77,7 @@ template <int MULTADD>
 __global__ void __launch_bounds__(128)
 k_prolong_add(double *__restrict__ uf, const double *__restrict__ uc, LevelDev F, LevelDev C, Stencil3 Pw)
 {
+	pdl_enter();
 	const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
 	const int i = blockIdx.y * blockDim.y + threadIdx.y;
 	if (i >= F.ni || j0 >= F.pitch) return;

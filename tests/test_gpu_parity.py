@@ -553,7 +553,8 @@ def test_csr_on_strips_concatenates_to_the_reference_matrix(ranks, aggl):
         o.close()
 
 
-@pytest.mark.parametrize("name", ["n129_l7_jacobi", "n101_l3_jacobi", "n1025_l10_jacobi", "n129_l7_cg_mg"])
+@pytest.mark.parametrize("name", ["n129_l7_jacobi", "n101_l3_jacobi", "n1025_l10_jacobi", "n129_l7_cg_mg",
+                                  "n129_l7_rbsor", "n129_l7_rbsor_w12", "n1025_l7_rbsor"])
 def test_without_bottom_kernel_matches_golden(name):
     """-mgb_bottom 0: the smallest levels go through the fused legs (down to 1 x 1) instead of the cluster kernel."""
     g = GOLD[name]
@@ -564,3 +565,17 @@ def test_without_bottom_kernel_matches_golden(name):
     assert np.allclose(r["rnorm"][ok], want[ok], rtol=RTOL, atol=RNORM_ATOL)
     if "-cycle 0" in g["options"]:
         assert hashlib.sha256(np.ascontiguousarray(r["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]
+
+
+@pytest.mark.parametrize("ksp,sweep", [("cg", ""), ("richardson", " -mg_levels_pc_sor_forward -mg_coarse_pc_sor_forward")])
+def test_pcmg_red_black_bottom_kernel_bit_identical_to_separate_launches(ksp, sweep):
+    """Cycle 8 with red-black SOR on every level and a Richardson+SOR coarse solver: the persistent bottom kernel (levels of
+    at most 63 rows, red-black half sweeps in place, MatInterpolateAdd order) gives the bits of the one-launch-per-half-sweep path."""
+    opts = (base(129, 7, mp=3).replace("-cycle 0", "-cycle 8") + f" -ksp_type {ksp} -ksp_rtol 1e-9 -mg_levels_ksp_type richardson "
+            "-mg_levels_pc_type sor -mg_levels_ksp_max_it 2 -mg_coarse_ksp_type richardson -mg_coarse_pc_type sor -mg_coarse_ksp_max_it 3" + sweep)
+    a = mgb.run_poisson(opts)
+    b = mgb.run_poisson(opts + " -mgb_bottom 0")
+    assert a["num_iter"] == b["num_iter"] and a["num_iter"] > 1
+    assert a["gpu_launches"] < b["gpu_launches"]                          # the bottom kernel really replaced launches
+    assert np.array_equal(a["u"], b["u"])
+    assert np.array_equal(a["rnorm"], b["rnorm"])

@@ -165,6 +165,7 @@ struct mgb_engine {
 	int bcast_done = -1;                     // level whose result a fused leg has just broadcast from inside the kernel
 	bool dead = false;                       // a ghost-row wait timed out: the ranks' version counters are out of step, the engine is unusable
 	int rb_fuse_min_rows = 2047;             // red-black SOR: levels with fewer rows take the one-sweep kernels (fuse_level; MGB_RB_FUSE_MIN_ROWS)
+	bool cg_fuse = true;                     // CG: direction update + operator apply + deferred x update in one pass (MGB_CG_FUSE=0: separate passes)
 	bool inkernel = true;                    // fused legs push / wait for their strip-to-strip rows themselves (MGB_INKERNEL_HALO=0: separate k_xfer launches)
 };
 #define LAUNCHED(e) do { (e)->launches++; } while (0)
@@ -380,6 +381,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	e->connected = (P == 1) || nlocal > 1;
 	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
 	{ const char *v = getenv("MGB_PDL"); if (v && v[0]) g_pdl = v[0] != '0'; }
+	{ const char *v = getenv("MGB_CG_FUSE"); if (v && v[0] == '0') e->cg_fuse = false; }
 	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }
@@ -1108,7 +1110,30 @@ static int k_apply_dot(mgb_engine *e, int l, int xv, int yv, int slot, int post_
 	}
 	return reduce_tail(e, l, nb, slot, 0, post_op);
 }
-// x += a p ; r -= a w ; scal[slot] = ||r||_2 in one pass (the CG update, mgb_blas.cuh: k_cg_update)
+static void swap_vec(mgb_engine *e, int l, int a, int b);
+// the CG direction step in one pass (mgb_stencil.cuh: k_cg_pstep): x += a_prev p ; p_new = z + b p (into the buffer of `nv`, then
+// p and nv swap) ; w = A p_new ; scal[slot] = p_new . w [+ TAIL_DPI].  Needs ghost rows of z and p to depth 1; leaves those of
+// the new p valid to depth 1 without an exchange.
+static int k_cg_dir(mgb_engine *e, int l, int zv, int pv, int nv, int wv, int xv, int slot, int post_op)
+{
+	TRY(flush_levels(e, l, l));
+	const LevelGeom &g = e->geo[l];
+	std::vector<int> nb;
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		SLevel &S = s.lev[l];
+		const int ry = pick_ry(g, S.ni);
+		const dim3 gr = stream_grid(g, S.ni, ry);
+		if ((size_t)gr.x * gr.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
+		klaunch(k_cg_pstep, dim3(gr), dim3(MGB_SB_THREADS), 0, s.stream, S.v[zv], S.v[pv], S.v[nv], S.v[wv], S.v[xv], ldev(e, s, l),
+		        s.scal + SC_RATIO, s.scal + SC_ALPHA, s.partial, ry);
+		LAUNCHED(e); KCHECK();
+		nb.push_back((int)(gr.x * gr.y));
+	}
+	swap_vec(e, l, pv, nv);
+	return reduce_tail(e, l, nb, slot, 0, post_op);
+}
+// x += a p ; r -= a w ; scal[slot] = ||r||_2 in one pass (the CG update, mgb_blas.cuh: k_cg_update); xv < 0: r and ||r|| only
 static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, double a, int slot, int a_slot = -1)
 {
 	const LevelGeom &g = e->geo[l];
@@ -1119,7 +1144,7 @@ static int k_cg_step(mgb_engine *e, int l, int xv, int pv, int rv, int wv, doubl
 		const size_t n2 = (size_t)S.ni * g.pitch / 2;
 		size_t want = (n2 + MGB_RED_THREADS * 4 - 1) / (MGB_RED_THREADS * 4);
 		const int blocks = (int)(want < 1 ? 1 : (want > MGB_RED_MAXBLOCKS ? MGB_RED_MAXBLOCKS : want));
-		klaunch(k_cg_update, dim3(blocks), dim3(MGB_RED_THREADS), 0, s.stream, S.v[xv], S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial, a_slot >= 0 ? s.scal + a_slot : nullptr);
+		klaunch(k_cg_update, dim3(blocks), dim3(MGB_RED_THREADS), 0, s.stream, xv >= 0 ? S.v[xv] : nullptr, S.v[pv], S.v[rv], S.v[wv], n2, a, s.partial, a_slot >= 0 ? s.scal + a_slot : nullptr);
 		LAUNCHED(e); KCHECK();
 		nb.push_back(blocks);
 	}
@@ -1609,6 +1634,26 @@ static int wait_gather(mgb_engine *e, int l)
 		a.ver = ver_of(e, s) + chan; a.ticket = ticket_of(e, s) + chan; a.status = status_of(e, s); a.status_host = s.status_host_dev;
 		a.spin_limit = e->spin_limit; a.do_push = 0; a.do_wait = 1;
 		for (int t = 1; t < e->P; ++t) a.wait_flag[a.nwait++] = flag_at(e, 0, chan, t);
+		k_xfer<<<1, 32, 0, s.stream>>>(a);
+		LAUNCHED(e); KCHECK();
+	}
+	return MGB_OK;
+}
+
+// the ghost rows of v[which] on level l were pushed by the neighbours from inside a fused leg: a consumer that cannot wait by
+// itself gets a wait-only launch on the channel (passes at once when the rows came by an ordinary exchange)
+static int wait_halo(mgb_engine *e, int l, int which)
+{
+	if (e->P == 1 || !e->geo[l].dist) return MGB_OK;
+	TRY(flush_levels(e, l, l));
+	for (auto &s : e->strips) {
+		if (!computes(s, l)) continue;
+		XferArgs a; memset(&a, 0, sizeof a);
+		const int chan = CH_HALO(l, s.lev[l].phys[which]);
+		a.ver = ver_of(e, s) + chan; a.ticket = ticket_of(e, s) + chan; a.status = status_of(e, s); a.status_host = s.status_host_dev;
+		a.spin_limit = e->spin_limit; a.do_push = 0; a.do_wait = 1;
+		if (s.rank > 0) a.wait_flag[a.nwait++] = flag_at(e, s.rank, chan, s.rank - 1);
+		if (s.rank < e->P - 1) a.wait_flag[a.nwait++] = flag_at(e, s.rank, chan, s.rank + 1);
 		k_xfer<<<1, 32, 0, s.stream>>>(a);
 		LAUNCHED(e); KCHECK();
 	}
@@ -2244,15 +2289,26 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 		if (!reason) {
 			TRY(vec_zero(e, Pv, 0));                                                               // p = 0: the first p = z + 0 p
 			for (auto &s : e->strips) { klaunch(k_set_scalar, dim3(1), dim3(1), 0, s.stream, s.scal + SC_BETA, INFINITY); LAUNCHED(e); KCHECK(); }
+			// the direction step fused with the operator apply and the deferred x update (k_cg_pstep); MGB_CG_FUSE=0: separate passes
+			const bool fuse_dir = e->cg_fuse;
+			if (fuse_dir) for (auto &s : e->strips) { klaunch(k_set_scalar, dim3(1), dim3(1), 0, s.stream, s.scal + SC_ALPHA, 0.0); LAUNCHED(e); KCHECK(); }
+			bool ran = false;
 			auto iteration = [&]() -> int {
 				bool dot_done = false;
 				TRY(halo(e, 0, R, HALO_DEPTH));
 				TRY(pcmg_cycle(e, p, 0, R, Z, 2, &dot_done));                                      // z = B r  [; beta = z'r]
 				if (!dot_done) TRY(k_reduce(e, 0, Z, R, 2, 0, TAIL_BETA));                         // beta = z'r ; b = beta / betaold
-				TRY(k_vecop<1>(e, 0, Pv, Z, 0.0, SC_RATIO));                                       // p = z + b p
-				TRY(halo(e, 0, Pv, 2));
-				TRY(k_apply_dot(e, 0, Pv, Q, 3, TAIL_DPI));                                        // w = A p ; dpi = p'w ; a = beta / dpi
-				TRY(k_cg_step(e, 0, X, Pv, R, Q, 0.0, 0, SC_ALPHA));                               // x += a p ; r -= a w ; ||r||
+				if (fuse_dir) {
+					// x += a_prev p ; p = z + b p ; w = A p ; dpi = p'w ; a = beta / dpi -- one pass, p's ghost rows derived locally
+					TRY(wait_halo(e, 0, Z));
+					TRY(k_cg_dir(e, 0, Z, Pv, MGB_VEC_W, Q, X, 3, TAIL_DPI));
+					TRY(k_cg_step(e, 0, -1, Pv, R, Q, 0.0, 0, SC_ALPHA));                              // r -= a w ; ||r||
+				} else {
+					TRY(k_vecop<1>(e, 0, Pv, Z, 0.0, SC_RATIO));                                       // p = z + b p
+					TRY(halo(e, 0, Pv, 2));
+					TRY(k_apply_dot(e, 0, Pv, Q, 3, TAIL_DPI));                                        // w = A p ; dpi = p'w ; a = beta / dpi
+					TRY(k_cg_step(e, 0, X, Pv, R, Q, 0.0, 0, SC_ALPHA));                               // x += a p ; r -= a w ; ||r||
+				}
 				return flush_all(e);
 			};
 			if (e->gcache.size() > 16) drop_graphs(e);
@@ -2267,6 +2323,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 				}
 				CU(cudaStreamSynchronize(s0.stream));
 				TRY(quick_status(e));
+				ran = true;
 				betaold = beta; dpiold = dpi;
 				beta = hs[SC_BETA]; dpi = hs[SC_DPI]; dp = hs[0];
 				if (beta == 0.0) { reason = 3; break; }
@@ -2278,6 +2335,7 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 				i++;
 			} while (i < p->max_iter);
 			if (i >= p->max_iter && !reason) reason = -3;                                          // KSP_DIVERGED_ITS
+			if (fuse_dir && ran) TRY(k_vecop<0>(e, 0, X, Pv, 0.0, SC_ALPHA));                      // the x += a p of the last iteration
 		}
 	} else {
 		// KSPSolve_Richardson, general path (residual norm logged every iteration), scale 1

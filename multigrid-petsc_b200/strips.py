@@ -127,7 +127,8 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn, bench):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     n = npts - 2
     steps, warm = a.steps, max(a.warmup, 3)
-    s = StripSession(options_fn(npts, levels, 1000))
+    aggl = int(os.environ.get("MGB_AGGLOMERATE", "0"))       # experiment knob: 0 = the engine's default (511 rows)
+    s = StripSession(options_fn(npts, levels, 1000), agglomerate=aggl)
     e = s.engine
     sm = _pkg.jacobi(0.8)
     e.solve_vcycle(sm, 3, 3, max_iter=warm, rtol=0.0)
@@ -226,7 +227,7 @@ def bench_strips(a, npts, levels, ClockSampler, hbm_peak, options_fn, bench):
                 "config": {"workload": bench.WORKLOAD,
                            "unknowns": n * n, "l2": "inputs larger than L2 on every strip at N<=4; per-strip fine vector "
                            f"{8.0 * n * n / world / 1e6:.0f} MB", "parallelism": f"{world} row strips, P2P ghost rows over NVLink, "
-                           "levels with <= 511 rows agglomerated on rank 0"},
+                           f"levels with <= {aggl or 511} rows agglomerated on rank 0"},
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "k_jfused<3,PRE_GIVEN,POST_RESTRICT> level 0 on every strip (+ its ghost-row exchange)", "achieved": ach,
                              "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world), "peak_kind": peak_kind + f" x {world} GPUs",

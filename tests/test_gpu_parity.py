@@ -579,3 +579,18 @@ def test_pcmg_red_black_bottom_kernel_bit_identical_to_separate_launches(ksp, sw
     assert a["gpu_launches"] < b["gpu_launches"]                          # the bottom kernel really replaced launches
     assert np.array_equal(a["u"], b["u"])
     assert np.array_equal(a["rnorm"], b["rnorm"])
+
+
+@pytest.mark.parametrize("extra", ["", " -mgb_ranks 2 -mgb_emulate 1 -mgb_agglomerate 31", " -mgb_ranks 4 -mgb_emulate 1 -mgb_agglomerate 31"])
+@pytest.mark.parametrize("name", ["n129_l7_cg_mg", "n129_l4_cg_mg_jcoarse"])
+def test_cg_fused_direction_step_bit_identical_to_separate_passes(name, extra, monkeypatch):
+    """CG: x += a p (deferred), p = z + b p, w = A p and p'w in one pass (k_cg_pstep; on strips the ghost rows of p are derived
+    locally instead of exchanged) against the separate VecAYPX / MatMult+VecDot / VecAXPY passes: same bits, same history."""
+    g = GOLD[name]
+    a = mgb.run_poisson(g["options"] + extra)
+    monkeypatch.setenv("MGB_CG_FUSE", "0")
+    b = mgb.run_poisson(g["options"] + extra)
+    assert a["num_iter"] == b["num_iter"] == g["num_iter"]
+    assert a["gpu_launches"] < b["gpu_launches"]
+    assert np.array_equal(a["rnorm"], b["rnorm"], equal_nan=True)
+    assert np.array_equal(a["u"], b["u"])

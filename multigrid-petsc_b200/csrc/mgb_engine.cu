@@ -47,6 +47,7 @@ static int fail(int code, const char *fmt, ...)
 	va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
 	return code;
 }
+extern "C" void mgb__set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }   // for mgb_sparse.cu
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) \
 	return fail(MGB_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); } while (0)
 #define TRY(call) do { int _r = (call); if (_r != MGB_OK) return _r; } while (0)

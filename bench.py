@@ -399,6 +399,75 @@ def b200_arm_cg(a, mgb):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------- per-level sweep
+def level_sweep(a, mgb):
+    """BASELINE configs[4], second half: smoother and residual bandwidth on EVERY level of the hierarchy, B200 kernels
+    (CUDA events, mgb_time_op) beside the reference's data path on the host cores (cpu_baseline leg: the CPU checker's
+    PETSc restatement -- assembled CSR MatMult + separate vector passes, OpenMP over all host threads)."""
+    import numpy as np
+    npts = a.npts
+    levels = cg_levels(npts)
+    n = npts - 2
+    e = mgb.Engine(levels, n)
+    e.set_poisson_uniform()
+    x = np.linspace(0, 1, npts)[1:-1]
+    e.set_rhs_separable(-2 * np.pi ** 2 * np.sin(np.pi * x), np.sin(np.pi * x))
+    e.solve_vcycle(mgb.jacobi(0.8), 3, 3, max_iter=2, rtol=0.0)          # non-trivial data on every level
+    l0 = e.launch_count()
+    peak, peak_kind = hbm_peak()
+    rows = []
+    for l in range(levels):
+        ni, nj = e.dims(l)
+        row = {"level": l, "n": ni}
+        for op in ("jacobi", "residual", "fused_down", "fused_up"):
+            if op.startswith("fused") and l == levels - 1:
+                continue
+            ms = e.time_op(op, l, a.steps)
+            bpu = mgb.FUSED_OWN_BYTES.get(op, mgb.OPS[op][1])
+            row[op] = {"us": ms * 1e3, "gbs": bpu * ni * nj / (ms * 1e-3) / 1e9, "frac": bpu * ni * nj / (ms * 1e-3) / 1e9 / peak}
+        rows.append(row)
+    launches = e.launch_count() - l0
+    e.close()
+    cpu = None
+    if not a.no_cpu_baseline:
+        from oracle import Oracle                                            # cpu_baseline leg (the checker as the CPU data path)
+        o = Oracle(options(npts, levels, 1))
+        cores = os.cpu_count() or 1
+        for l, row in enumerate(rows):
+            ni, nj = o.dims(l)
+            rng = np.random.default_rng(l)
+            b = rng.standard_normal(ni * nj); xx = rng.standard_normal(ni * nj)
+            reps = 2 if ni > 4000 else (5 if ni > 1000 else 20)
+            o.smooth(l, b, xx, 1, False); o.residual(l, b, xx)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                o.smooth(l, b, xx, 1, False)
+            t1 = time.perf_counter()
+            for _ in range(reps):
+                o.residual(l, b, xx)
+            t2 = time.perf_counter()
+            # bytes of the CSR data path per unknown: MatMult 80 (SURVEY 8d) + the vector passes of one Richardson+Jacobi
+            # iteration (r = b - t: 24, z = r * dinv: 24, x += s z: 24) resp. of KSPBuildResidual (24)
+            row["cpu_jacobi"] = {"us": (t1 - t0) / reps * 1e6, "gbs": 152.0 * ni * nj / ((t1 - t0) / reps) / 1e9}
+            row["cpu_residual"] = {"us": (t2 - t1) / reps * 1e6, "gbs": 104.0 * ni * nj / ((t2 - t1) / reps) / 1e9}
+            row["speedup_jacobi"] = row["cpu_jacobi"]["us"] / row["jacobi"]["us"]
+            row["speedup_residual"] = row["cpu_residual"]["us"] / row["residual"]["us"]
+        o.close()
+        cpu = {"value": rows[0]["cpu_jacobi"]["gbs"], "unit": "GB/s (fine-level Jacobi sweep, CSR data path: 152 B/unknown)", "cores": cores, "kind": "port",
+               "sample": f"one smoother sweep and one residual on every level of the {npts}^2 hierarchy, 2-20 repetitions each, the CPU "
+                         "checker's PETSc restatement (mini-PETSc, not real PETSc) incl. one vector copy per call"}
+    line = {"metric": "smoother / residual HBM GB/s per level (fp64)", "value": rows[0]["jacobi"]["gbs"], "unit": "GB/s", "n_gpus": 1,
+            "steps": a.steps, "warmup": 2, "ms_per_step": rows[0]["jacobi"]["us"] / 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"per-level smoother / residual bandwidth sweep, {npts}^2, {levels} levels (BASELINE configs[4])",
+                       "unknowns": n * n, "l2": "levels above 2047^2 exceed L2; smaller levels are L2-resident (stated per row by n)"},
+            "roofline": {"bound": "hbm", "kernel": "k_stream5<ST_JACOBI> level 0", "achieved": rows[0]["jacobi"]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": rows[0]["jacobi"]["frac"], "peak_kind": peak_kind, "traffic": None},
+            "levels": rows, "cpu_baseline": cpu, "gpu_launches": int(launches)}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 # ---------------------------------------------------------------------------------------------- B200 arm
 def b200_arm(a):
     import numpy as np
@@ -414,6 +483,8 @@ def b200_arm(a):
     mgb = importlib.import_module("multigrid-petsc_b200")
     if a.workload == "cg":
         return b200_arm_cg(a, mgb)
+    if a.workload == "sweep":
+        return level_sweep(a, mgb)
     if a.workload == "weak":
         strips = importlib.import_module("multigrid-petsc_b200.strips")
         return strips.bench_weak(a, ClockSampler, hbm_peak)
@@ -533,7 +604,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="strong", choices=["strong", "weak", "cg"],
+    ap.add_argument("--workload", default="strong", choices=["strong", "weak", "cg", "sweep"],
                     help="strong (default): 8193^2 split over the GPUs (BASELINE configs[3]); weak: 4096 x 4097 points per GPU (configs[4]); "
                          "cg: MG-preconditioned CG to 1e-10 (configs[2] and the north-star time-to-solution), --npts 4097|8193")
     ap.add_argument("--npts", type=int, default=8193, help="grid points per side for --workload cg")

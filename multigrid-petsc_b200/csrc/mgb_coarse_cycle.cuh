@@ -235,10 +235,12 @@ __device__ __forceinline__ void cc_smooth(const CoarseArgs &A, const CLevel &L, 
 }
 
 // the whole sub-cycle of levels lo .. nlev-1 inside ONE CTA with everything in shared memory (levels of at most
-// CC_TINY rows): __syncthreads between phases instead of cluster barriers and L2 round trips
+// CC_TINY rows): __syncthreads between phases instead of cluster barriers and L2 round trips.  (Measured, round 2: taking the
+// 63-row level in here as well -- 152 KB of shared memory, one SM instead of eight -- is slower by ~11 us per cycle.)
 #define CC_TINY 31
 #define CC_TINY_DOUBLES 1792              // per vector, all tiny levels together (ghost row above and below each level)
 #define CC_TINY_COEF 512                  // coefficient rows of all tiny levels (8 doubles per grid row)
+#define CC_SMEM_BYTES ((3 * CC_TINY_DOUBLES + CC_TINY_COEF) * sizeof(double))     // 46 KB of dynamic shared memory
 template <int MULTADD, bool RB>
 __device__ void tiny_cycle(const CoarseArgs &A, int lo, double *sx, double *sw, double *sb, double *sc, const ccy::Rows &R)
 {
@@ -344,7 +346,8 @@ __global__ void __cluster_dims__(CC_CTAS, 1, 1) __launch_bounds__(CC_THREADS)
 k_coarse_cycle(CoarseArgs A)
 {
 	pdl_enter();
-	__shared__ double sx[CC_TINY_DOUBLES], sw[CC_TINY_DOUBLES], sb[CC_TINY_DOUBLES], sc[CC_TINY_COEF];
+	extern __shared__ __align__(16) double cc_smem[];
+	double *sx = cc_smem, *sw = sx + CC_TINY_DOUBLES, *sb = sw + CC_TINY_DOUBLES, *sc = sb + CC_TINY_DOUBLES;
 	if (A.rb) coarse_cycle_body<true>(A, sx, sw, sb, sc);
 	else      coarse_cycle_body<false>(A, sx, sw, sb, sc);
 }

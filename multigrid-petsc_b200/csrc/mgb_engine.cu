@@ -166,6 +166,8 @@ struct mgb_engine {
 	int bcast_done = -1;                     // level whose result a fused leg has just broadcast from inside the kernel
 	bool dead = false;                       // a ghost-row wait timed out: the ranks' version counters are out of step, the engine is unusable
 	int rb_fuse_min_rows = 2047;             // red-black SOR: levels with fewer rows take the one-sweep kernels (fuse_level; MGB_RB_FUSE_MIN_ROWS)
+	int boundary_chunks = 1;                 // strips: short first / last row chunks in the fused legs (MGB_BOUNDARY_CHUNKS=0: uniform chunks,
+	                                         // 2: also where the interior chunks are short -- tests)
 	bool cg_fuse = true;                     // CG: direction update + operator apply + deferred x update in one pass (MGB_CG_FUSE=0: separate passes)
 	bool inkernel = true;                    // fused legs push / wait for their strip-to-strip rows themselves (MGB_INKERNEL_HALO=0: separate k_xfer launches)
 };
@@ -383,6 +385,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
 	{ const char *v = getenv("MGB_PDL"); if (v && v[0]) g_pdl = v[0] != '0'; }
 	{ const char *v = getenv("MGB_CG_FUSE"); if (v && v[0] == '0') e->cg_fuse = false; }
+	{ const char *v = getenv("MGB_BOUNDARY_CHUNKS"); if (v && v[0]) e->boundary_chunks = atoi(v); }
 	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }
@@ -1612,8 +1615,8 @@ static void fused_comm(mgb_engine *e, Strip &s, int l, int D, int pre_k, int pos
 	if (X.nch) {
 		int chunks = 0;
 		const int ni = s.lev[l].ni;
-		for (int y0 = 0; y0 < ni; y0 += a.rows) {
-			const int y1 = y0 + a.rows < ni ? y0 + a.rows : ni;
+		for (int by = 0; by < (int)grid.y; ++by) {
+			int y0, y1; jf_chunk(a.hb, a.rows, ni, by, &y0, &y1);
 			bool takes = X.bc_remote && post_k == POST_RESTRICT;
 			for (int k = 0; k < X.npu; ++k) takes |= (D > 0 && y0 < X.pu[k].hi && y1 > X.pu[k].lo);
 			for (int k = 0; k < X.npb; ++k) takes |= (post_k == POST_RESTRICT && (y0 >> 1) < X.pb[k].hi && (y1 >> 1) > X.pb[k].lo);
@@ -1698,6 +1701,16 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			a.F = fused_ldev(e, s, l); a.scale = rb ? sm->omega : sm->scale; a.gni = g.gni;
 			for (int k = 0; k < D; ++k) if (stages[done + k] == 1) a.rbmask |= 1 << k;
 			a.rows = pick_rows(g, S.ni);
+			// strips: short boundary chunks (2 x HALO_DEPTH rows: the pushed rows of u and of the restricted right-hand side)
+			// where the interior chunks are at least twice as long, so that the boundary blocks are never the last to finish
+			if (inkernel && g.dist && e->boundary_chunks && (a.rows >= 4 * HALO_DEPTH || e->boundary_chunks >= 2) && S.ni >= 8 * HALO_DEPTH) {
+				a.hb = 2 * HALO_DEPTH;
+				const int inner = S.ni - 2 * a.hb;
+				int chunks = (148 * (512 / FJ_THREADS)) / cdiv(g.pitch, FJ_VALID) - 2;
+				if (chunks < 1) chunks = 1;
+				a.rows = (cdiv(inner, chunks) + 1) & ~1;
+				if (a.rows < 4) a.rows = 4;
+			}
 			a.R3 = e->R3; a.P3 = e->P3;
 			int tiles = cdiv(g.pitch, FJ_VALID);
 			if (pre_k == PRE_PROLONG || pre_k == PRE_PROLONG_MULTADD) {
@@ -1710,7 +1723,7 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 				const int need = cdiv(2 * e->geo[l + 1].pitch, FJ_VALID);
 				if (need > tiles) tiles = need;
 			}
-			dim3 grid(tiles, cdiv(S.ni, a.rows));
+			dim3 grid(tiles, jf_nchunks(a.hb, a.rows, S.ni));
 			if (post_k == POST_NORM || post_k == POST_DOT) {
 				if ((size_t)grid.x * grid.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
 				a.partial = s.partial;
@@ -1785,7 +1798,15 @@ static int bottom_cycle(mgb_engine *e, int lp, const mgb_smoother *sm_level, int
 				c.scale = last ? sm_coarse->scale : sm_level->scale;
 			}
 		}
-		klaunch(k_coarse_cycle, dim3(CC_CTAS), dim3(CC_THREADS), 0, s.stream, a);
+		{
+			// 152 KB of dynamic shared memory: opt-in once per device (as in launch_jfused)
+			static std::mutex mu; static bool optin[64] = {};
+			int dev = 0; cudaGetDevice(&dev);
+			std::lock_guard<std::mutex> lk(mu);
+			if (dev >= 0 && dev < 64 && !optin[dev] &&
+			    cudaFuncSetAttribute(k_coarse_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC_SMEM_BYTES) == cudaSuccess) optin[dev] = true;
+		}
+		klaunch(k_coarse_cycle, dim3(CC_CTAS), dim3(CC_THREADS), CC_SMEM_BYTES, s.stream, a);
 		LAUNCHED(e); KCHECK();
 	}
 	if (!rb)                                                  // red-black half sweeps are in place: no ping-pong

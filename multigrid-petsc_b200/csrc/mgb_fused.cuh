@@ -119,10 +119,29 @@ struct FusedArgs {
 	Stencil3 R3, P3;
 	double scale;
 	int rows;                // rows per block (even)
+	int hb;                  // > 0 (strips): blockIdx.y 0 / 1 own the first hb / the last ~hb rows (the rows whose results travel to the
+	                         // neighbours and whose inputs come from them), the other blocks split the rows in between: the two
+	                         // short boundary chunks finish -- and push -- early, and a late ghost row delays only them
 	int gni;                 // global number of rows of the fine level
 	int rbmask;              // red-black stages (SMK = 1): bit s-1 = colour updated by stage s (0 red = (i+j) even, 1 black); scale = omega
 	FusedComm X;             // all zero on a single strip
 };
+
+// rows [y0, y1) of row chunk `by` of `nby` (host and device use the same mapping; hb even, rows even)
+__host__ __device__ __forceinline__ void jf_chunk(int hb, int rows, int ni, int by, int *y0, int *y1)
+{
+	if (hb <= 0) { *y0 = by * rows; *y1 = (*y0 + rows < ni) ? *y0 + rows : ni; return; }
+	const int yb = (ni - hb) & ~1;                 // first row of the bottom boundary chunk (even: restriction pairs rows)
+	if (by == 0) { *y0 = 0; *y1 = hb; }
+	else if (by == 1) { *y0 = yb; *y1 = ni; }
+	else { *y0 = hb + (by - 2) * rows; *y1 = (*y0 + rows < yb) ? *y0 + rows : yb; }
+}
+__host__ __device__ __forceinline__ int jf_nchunks(int hb, int rows, int ni)
+{
+	if (hb <= 0) return (ni + rows - 1) / rows;
+	const int yb = (ni - hb) & ~1;
+	return 2 + (yb - hb + rows - 1) / rows;
+}
 
 struct Coef { double aS, aW, aC, aE, aN, dinv, nS; };   // nS = -aS (power-of-two path)
 template <int SMK = 0>
@@ -610,8 +629,7 @@ k_jfused(FusedArgs A)
 	B.tid = threadIdx.x;
 	B.c0 = blockIdx.x * FJ_VALID;                         // first valid column of the tile
 	B.j0 = B.c0 - FJ_HALO + 2 * B.tid;                    // this thread's columns j0, j0+1 (j0 even)
-	B.y0 = blockIdx.y * A.rows;
-	B.y1 = min(B.y0 + A.rows, F.ni);
+	jf_chunk(A.hb, A.rows, F.ni, (int)blockIdx.y, &B.y0, &B.y1);
 	B.P = (ptrdiff_t)F.pitch;
 	B.in0 = B.j0 >= 0 && B.j0 < F.nj; B.in1 = B.j0 + 1 >= 0 && B.j0 + 1 < F.nj;
 	B.ld_ok = B.j0 >= 0 && B.j0 < F.pitch;                // the pair may be loaded (pad columns hold zeros)

@@ -167,9 +167,6 @@ struct mgb_engine {
 	int bcast_done = -1;                     // level whose result a fused leg has just broadcast from inside the kernel
 	bool dead = false;                       // a ghost-row wait timed out: the ranks' version counters are out of step, the engine is unusable
 	int rb_fuse_min_rows = 2047;             // red-black SOR: levels with fewer rows take the one-sweep kernels (fuse_level; MGB_RB_FUSE_MIN_ROWS)
-	int boundary_chunks = 0;                 // strips: the first / last row chunk of a fused leg in two passes, boundary rows first, so that their
-	                                         // pushes leave early (MGB_BOUNDARY_CHUNKS=1; 2: also on short chunks -- tests).  Off by default:
-	                                         // measured at 2 GPUs it hides nothing that matters (1276 against 1317 V-cycles/s)
 	bool cg_fuse = true;                     // CG: direction update + operator apply + deferred x update in one pass (MGB_CG_FUSE=0: separate passes)
 	bool inkernel = true;                    // fused legs push / wait for their strip-to-strip rows themselves (MGB_INKERNEL_HALO=0: separate k_xfer launches)
 };
@@ -387,7 +384,6 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
 	{ const char *v = getenv("MGB_PDL"); if (v && v[0]) g_pdl = v[0] != '0'; }
 	{ const char *v = getenv("MGB_CG_FUSE"); if (v && v[0] == '0') e->cg_fuse = false; }
-	{ const char *v = getenv("MGB_BOUNDARY_CHUNKS"); if (v && v[0]) e->boundary_chunks = atoi(v); }
 	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }
@@ -1617,15 +1613,13 @@ static void fused_comm(mgb_engine *e, Strip &s, int l, int D, int pre_k, int pos
 	if (X.nch) {
 		int chunks = 0;
 		const int ni = s.lev[l].ni;
-		for (int by = 0; by < (int)grid.y; ++by)
-			for (int pass = 0; pass < jf_npass(a.hb, (int)grid.y, by); ++pass) {      // one ticket per (chunk, pass) that pushes
-				int y0, y1; jf_chunk(a.hb, a.rows, ni, (int)grid.y, by, pass, &y0, &y1);
-				if (y0 >= y1) continue;
-				bool takes = X.bc_remote && post_k == POST_RESTRICT;
-				for (int k = 0; k < X.npu; ++k) takes |= (D > 0 && y0 < X.pu[k].hi && y1 > X.pu[k].lo);
-				for (int k = 0; k < X.npb; ++k) takes |= (post_k == POST_RESTRICT && (y0 >> 1) < X.pb[k].hi && (y1 >> 1) > X.pb[k].lo);
-				chunks += takes ? 1 : 0;
-			}
+		for (int y0 = 0; y0 < ni; y0 += a.rows) {
+			const int y1 = y0 + a.rows < ni ? y0 + a.rows : ni;
+			bool takes = X.bc_remote && post_k == POST_RESTRICT;
+			for (int k = 0; k < X.npu; ++k) takes |= (D > 0 && y0 < X.pu[k].hi && y1 > X.pu[k].lo);
+			for (int k = 0; k < X.npb; ++k) takes |= (post_k == POST_RESTRICT && (y0 >> 1) < X.pb[k].hi && (y1 >> 1) > X.pb[k].lo);
+			chunks += takes ? 1 : 0;
+		}
 		X.npushblocks = chunks * (int)grid.x;
 		X.ticket = ticket_of(e, s) + first_chan;
 		if (X.npushblocks == 0) X.nch = 0;
@@ -1705,16 +1699,6 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 			a.F = fused_ldev(e, s, l); a.scale = rb ? sm->omega : sm->scale; a.gni = g.gni;
 			for (int k = 0; k < D; ++k) if (stages[done + k] == 1) a.rbmask |= 1 << k;
 			a.rows = pick_rows(g, S.ni);
-			// strips: the first and the last row chunk run in two passes, the 2 x HALO_DEPTH rows at the strip boundary first
-			// (jf_chunk in mgb_fused.cuh): their pushes leave while the rest of the strip is still being computed.  Only where
-			// the chunks are long enough for the second pass to be worth its warm-up rows (forced everywhere by the tests).
-			{
-				const int hb = 2 * HALO_DEPTH;
-				const int slots = std::max(3, (148 * (512 / FJ_THREADS)) / cdiv(g.pitch, FJ_VALID));
-				int rows2 = (cdiv(S.ni + 2 * hb, slots) + 1) & ~1;            // 2 (rows - hb) + (slots - 2) rows >= ni
-				if (e->boundary_chunks >= 2 && rows2 < 2 * hb + 4) rows2 = 2 * hb + 4;
-				if (inkernel && g.dist && e->boundary_chunks && rows2 >= 2 * hb + 4 && S.ni >= 2 * (rows2 - hb) + 2) { a.hb = hb; a.rows = rows2; }
-			}
 			a.R3 = e->R3; a.P3 = e->P3;
 			int tiles = cdiv(g.pitch, FJ_VALID);
 			if (pre_k == PRE_PROLONG || pre_k == PRE_PROLONG_MULTADD) {
@@ -1727,12 +1711,11 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 				const int need = cdiv(2 * e->geo[l + 1].pitch, FJ_VALID);
 				if (need > tiles) tiles = need;
 			}
-			dim3 grid(tiles, jf_nchunks(a.hb, a.rows, S.ni));
+			dim3 grid(tiles, cdiv(S.ni, a.rows));
 			if (post_k == POST_NORM || post_k == POST_DOT) {
-				const size_t np = (size_t)grid.x * (grid.y + (a.hb > 0 ? 2 : 0));    // two-pass boundary chunks: one more slot each
-				if (np > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
+				if ((size_t)grid.x * grid.y > s.partial_cap) return fail(MGB_EINVAL, "grid too large for the partial-sum buffer");
 				a.partial = s.partial;
-				nb.push_back((int)np);
+				nb.push_back((int)(grid.x * grid.y));
 			}
 			if (inkernel) fused_comm(e, s, l, D, pre_k, post_k, bv, xv, S.phys[sv], bcast_k, grid, a);
 			int rc;

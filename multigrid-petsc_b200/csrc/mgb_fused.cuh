@@ -119,34 +119,10 @@ struct FusedArgs {
 	Stencil3 R3, P3;
 	double scale;
 	int rows;                // rows per block (even)
-	int hb;                  // > 0 (strips): the first / last row chunk run in two passes, the hb rows at the strip boundary first (jf_chunk):
-	                         // their pushes leave while the rest of the strip is still being computed
 	int gni;                 // global number of rows of the fine level
 	int rbmask;              // red-black stages (SMK = 1): bit s-1 = colour updated by stage s (0 red = (i+j) even, 1 black); scale = omega
 	FusedComm X;             // all zero on a single strip
 };
-
-// Row chunks.  hb == 0: chunk `by` owns rows [by * rows, (by + 1) * rows).  hb > 0 (strips): the first and the last chunk own
-// rows_b = rows - hb rows and process them in TWO passes, the hb rows next to the strip boundary first -- their results are
-// what the neighbours wait for, and they are the only rows computed from ghost data -- then the rest; a pass costs D + 9
-// warm-up steps, so with rows_b = rows - hb every block runs about the same number of steps.  Host and device share this.
-__host__ __device__ __forceinline__ int jf_npass(int hb, int nby, int by) { return (hb > 0 && (by == 0 || by == nby - 1)) ? 2 : 1; }
-__host__ __device__ __forceinline__ void jf_chunk(int hb, int rows, int ni, int nby, int by, int pass, int *y0, int *y1)
-{
-	if (hb <= 0) { *y0 = by * rows; *y1 = (*y0 + rows < ni) ? *y0 + rows : ni; return; }
-	const int rows_b = rows - hb;
-	const int yb = (ni - rows_b) & ~1;             // first row of the last chunk (even: restriction pairs rows)
-	const int ye = (ni - hb) & ~1;                 // first row of its boundary part
-	if (by == 0) { if (pass == 0) { *y0 = 0; *y1 = hb; } else { *y0 = hb; *y1 = rows_b; } }
-	else if (by == nby - 1) { if (pass == 0) { *y0 = ye; *y1 = ni; } else { *y0 = yb; *y1 = ye; } }
-	else { *y0 = rows_b + (by - 1) * rows; *y1 = (*y0 + rows < yb) ? *y0 + rows : yb; }
-}
-__host__ __device__ __forceinline__ int jf_nchunks(int hb, int rows, int ni)
-{
-	if (hb <= 0) return (ni + rows - 1) / rows;
-	const int rows_b = rows - hb, yb = (ni - rows_b) & ~1;
-	return 2 + (yb - rows_b + rows - 1) / rows;
-}
 
 struct Coef { double aS, aW, aC, aE, aN, dinv, nS; };   // nS = -aS (power-of-two path)
 template <int SMK = 0>
@@ -253,7 +229,6 @@ struct JfBlock {
 	Coef cu;                 // coefficients of a uniform operator, held in ordinary (per-thread) registers
 	double scale;
 	double sd;               // scale * dinv (power-of-two operator: exact, see jf_point)
-	int pidx;                // slot of this (block, pass) in the partial-sum buffer (POST_NORM / POST_DOT)
 };
 
 // One Jacobi update / residual at a point.  OP = 0: per-row coefficients, 1: one coefficient set, 2: one set with
@@ -593,7 +568,7 @@ __device__ __forceinline__ void jf_run(const FusedArgs &A, const JfBlock &B, dou
 	}
 	if (POST == POST_NORM || POST == POST_DOT) {
 		const double s = block_sum<FJ_THREADS>(S.acc);
-		if (B.tid == 0) A.partial[B.pidx] = s;
+		if (B.tid == 0) A.partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 	}
 }
 
@@ -635,6 +610,8 @@ k_jfused(FusedArgs A)
 	B.tid = threadIdx.x;
 	B.c0 = blockIdx.x * FJ_VALID;                         // first valid column of the tile
 	B.j0 = B.c0 - FJ_HALO + 2 * B.tid;                    // this thread's columns j0, j0+1 (j0 even)
+	B.y0 = blockIdx.y * A.rows;
+	B.y1 = min(B.y0 + A.rows, F.ni);
 	B.P = (ptrdiff_t)F.pitch;
 	B.in0 = B.j0 >= 0 && B.j0 < F.nj; B.in1 = B.j0 + 1 >= 0 && B.j0 + 1 < F.nj;
 	B.ld_ok = B.j0 >= 0 && B.j0 < F.pitch;                // the pair may be loaded (pad columns hold zeros)
@@ -645,30 +622,6 @@ k_jfused(FusedArgs A)
 		B.cu.dinv = vreg(c.dinv); B.cu.nS = vreg(c.nS);
 		B.scale = vreg(SMK ? sub(1.0, A.scale) : A.scale);    // red-black: 1 - omega (A.scale carries omega)
 		B.sd = vreg(A.scale * c.dinv);
-	}
-	B.g_u = A.u_in + (B.c0 - FJ_HALO); B.g_b = A.b + (B.c0 - FJ_HALO);
-	const int npass = jf_npass(A.hb, (int)gridDim.y, (int)blockIdx.y);
-	for (int pass = 0; pass < npass; ++pass) {
-	jf_chunk(A.hb, A.rows, F.ni, (int)gridDim.y, (int)blockIdx.y, pass, &B.y0, &B.y1);
-	B.pidx = (pass == 0) ? (int)(blockIdx.y * gridDim.x + blockIdx.x)
-	                     : (int)((gridDim.y + (blockIdx.y == 0 ? 0u : 1u)) * gridDim.x + blockIdx.x);
-	if (pass > 0) {
-		// second pass of a boundary chunk: every copy of the first pass has landed (jf_run drains its requests); the ring
-		// barriers start over at phase 0
-		cp_async_wait<0>();
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			for (int k = 0; k < FJ_NR; ++k) {
-				asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(B.s_bar + 8u * (unsigned)k) : "memory");
-				mbar_init(B.bar + k, 1);
-			}
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		}
-		__syncthreads();
-	}
-	if (B.y0 >= B.y1) {                                   // an empty second pass still owns a partial-sum slot
-		if ((POST == POST_NORM || POST == POST_DOT) && threadIdx.x == 0) A.partial[B.pidx] = 0.0;
-		continue;
 	}
 	// steps: stage 0 of row y0-D-1 is the first needed, the restriction of row y1 completes at step y1+D+3;
 	// the first step is rounded down to a multiple of four (ring slots are compile-time functions of t & 3)
@@ -684,6 +637,7 @@ k_jfused(FusedArgs A)
 		}
 		__syncthreads();
 	}
+	B.g_u = A.u_in + (B.c0 - FJ_HALO); B.g_b = A.b + (B.c0 - FJ_HALO);
 	// interior blocks: every row and column this block touches lies inside the grid and inside this strip's arrays
 	const bool interior = (B.c0 - FJ_HALO >= 0) && (B.c0 - FJ_HALO + FJ_COLS <= F.nj) &&
 	                      (F.i0 + tb - 1 >= 0) && (F.i0 + te + 4 + FJ_PF < A.gni) && (tb - 1 >= -MGB_GHOST_ROWS) &&
@@ -740,5 +694,4 @@ k_jfused(FusedArgs A)
 			}
 		}
 	}
-	}   // pass
 }

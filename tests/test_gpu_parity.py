@@ -594,24 +594,3 @@ def test_cg_fused_direction_step_bit_identical_to_separate_passes(name, extra, m
     assert a["gpu_launches"] < b["gpu_launches"]
     assert np.array_equal(a["rnorm"], b["rnorm"], equal_nan=True)
     assert np.array_equal(a["u"], b["u"])
-
-
-@pytest.mark.parametrize("name,ranks,aggl", [("n1025_l10_jacobi", 4, 0), ("n1025_l10_jacobi", 8, 63), ("n129_l7_cg_mg", 2, 31), ("n1025_l7_rbsor", 4, 127)])
-def test_strips_boundary_row_chunks_bit_identical(name, ranks, aggl, monkeypatch):
-    """Strips: the fused legs give the rows that travel to the neighbours (and the rows computed from ghost data) to two short
-    row chunks of their own, scheduled first (FusedArgs.hb).  Forced on every distributed level here (MGB_BOUNDARY_CHUNKS=2; by
-    default only where the interior chunks are long): the partition of rows over blocks changes, the values do not."""
-    g = GOLD[name]
-    extra = f" -mgb_ranks {ranks} -mgb_emulate 1" + (f" -mgb_agglomerate {aggl}" if aggl else "")
-    monkeypatch.setenv("MGB_BOUNDARY_CHUNKS", "2")
-    a = mgb.run_poisson(g["options"] + extra)
-    monkeypatch.setenv("MGB_BOUNDARY_CHUNKS", "0")
-    b = mgb.run_poisson(g["options"] + extra)
-    assert a["num_iter"] == b["num_iter"] == g["num_iter"]
-    if "-cycle 0" in g["options"]:
-        assert np.array_equal(a["u"], b["u"])
-        assert hashlib.sha256(np.ascontiguousarray(a["u"], dtype="<f8").tobytes()).hexdigest() == g["u_sha256"]
-    else:                                                                # CG: the dot products are summed over other blocks
-        assert np.abs(a["u"] - b["u"]).max() <= RTOL * np.abs(b["u"]).max()
-    want = _hex(g["rnorm_hex"]); ok = ~np.isnan(want)
-    assert np.allclose(a["rnorm"][ok], want[ok], rtol=RTOL, atol=RNORM_ATOL)

@@ -179,21 +179,25 @@ __global__ void k_sp_red2(const double *__restrict__ part, int nb, double *__res
 	for (int b = 0; b < nb; ++b) s = (MODE == 2) ? fmax(s, part[b]) : add(s, part[b]);
 	out[0] = s;
 }
+// scratch of the reductions (block sums + the result), grown on demand and kept: a VecNorm per cycle must not cost a cudaMalloc
+static double *g_red_part = nullptr; static int g_red_cap = 0;
 static int reduce(int mode, const mgb_dvec *x, const mgb_dvec *y, double *out)
 {
 	const int n = x->n, nb = (n + SP_RED_BLK - 1) / SP_RED_BLK;
 	if (n == 0) { *out = 0.0; return MGB_OK; }
-	double *part = nullptr;
-	SCU(cudaMalloc(&part, sizeof(double) * (size_t)(nb + 1)));
+	if (nb + 1 > g_red_cap) {
+		cudaFree(g_red_part); g_red_part = nullptr; g_red_cap = 0;
+		SCU(cudaMalloc(&g_red_part, sizeof(double) * (size_t)(2 * nb + 2)));
+		g_red_cap = 2 * nb + 2;
+	}
+	double *part = g_red_part;
 	const int gr = (nb + 127) / 128;
 	if (mode == 0) { k_sp_red1<0><<<gr, 128>>>(x->d, y->d, n, part); k_sp_red2<0><<<1, 1>>>(part, nb, part + nb); }
 	else if (mode == 1) { k_sp_red1<1><<<gr, 128>>>(x->d, nullptr, n, part); k_sp_red2<1><<<1, 1>>>(part, nb, part + nb); }
 	else { k_sp_red1<2><<<gr, 128>>>(x->d, nullptr, n, part); k_sp_red2<2><<<1, 1>>>(part, nb, part + nb); }
 	SLAUNCHED(); SLAUNCHED();
-	cudaError_t e = cudaGetLastError();
-	if (e == cudaSuccess) e = cudaMemcpy(out, part + nb, sizeof(double), cudaMemcpyDeviceToHost);
-	cudaFree(part);
-	if (e != cudaSuccess) return sfail(MGB_ECUDA, "reduction failed: %s", cudaGetErrorString(e));
+	SKCHECK();
+	SCU(cudaMemcpy(out, part + nb, sizeof(double), cudaMemcpyDeviceToHost));
 	return MGB_OK;
 }
 extern "C" int mgb_dvec_dot(const mgb_dvec *x, const mgb_dvec *y, double *out)

@@ -163,6 +163,7 @@ struct mgb_engine {
 	std::vector<struct GraphEntry> gcache;   // instantiated V-cycle graphs, keyed by parameters + pointer state
 	long long spin_limit = 8000000000LL;     // ~4 s at 2 GHz
 	int coarse_threshold = 63;               // levels with at most this many rows run in the persistent bottom kernel
+	int rb_coarse_threshold = 63;            // ... with red-black SOR (MGB_RB_BOTTOM_ROWS, experiment knob)
 	std::vector<XferReq> pending;            // deferred transfer requests (see flush_levels)
 	int bcast_done = -1;                     // level whose result a fused leg has just broadcast from inside the kernel
 	bool dead = false;                       // a ghost-row wait timed out: the ranks' version counters are out of step, the engine is unusable
@@ -384,6 +385,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	{ const char *v = getenv("MGB_INKERNEL_HALO"); if (v && v[0] == '0') e->inkernel = false; }
 	{ const char *v = getenv("MGB_PDL"); if (v && v[0]) g_pdl = v[0] != '0'; }
 	{ const char *v = getenv("MGB_CG_FUSE"); if (v && v[0] == '0') e->cg_fuse = false; }
+	{ const char *v = getenv("MGB_RB_BOTTOM_ROWS"); if (v && v[0]) e->rb_coarse_threshold = atoi(v); }
 	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }
@@ -1749,11 +1751,14 @@ static int fused_leg(mgb_engine *e, int l, const mgb_smoother *sm, int its, int 
 // ------------------------------------------------------------------------------------------------ persistent bottom of the cycle
 // first level handled by k_coarse_cycle: the finest level l >= 1 that is whole on rank 0 and has at most
 // coarse_threshold rows (L if there is none or the bottom has too many levels for one launch)
-static int bottom_start(const mgb_engine *e)
+// (Measured for red-black SOR at 1025^2 / 7 levels, MGB_RB_BOTTOM_ROWS: cluster kernel from 63 rows 4.0-4.1 k cycles/s, from 127
+// rows 3.6 k, from 255 rows 2.9 k -- 16 cluster phases per level cost more than 17 one-sweep launches of ~3 us; 63 for both smoothers.)
+static int bottom_start(const mgb_engine *e, const mgb_smoother *sm)
 {
 	if (e->coarse_threshold <= 0) return e->L;
+	const int thr = (sm && sm->type == MGB_SMOOTH_RBSOR) ? e->rb_coarse_threshold : e->coarse_threshold;
 	for (int l = 1; l < e->L; ++l)
-		if (!e->geo[l].dist && e->geo[l].gni <= e->coarse_threshold && e->geo[l].nj <= 2 * e->coarse_threshold)
+		if (!e->geo[l].dist && e->geo[l].gni <= thr && e->geo[l].nj <= 2 * thr)
 			return (e->L - l <= CC_MAXLEV) ? l : e->L;
 	return e->L;
 }
@@ -1962,7 +1967,7 @@ static int vcycle_body(mgb_engine *e, const mgb_vcycle_params *p, bool first)
 			TRY(fused_leg(e, 0, s, p->v0, first ? PRE_ZERO : PRE_GIVEN, POST_NORM, B, U, W, 0));
 		} else {
 			// levels lp .. Lc-1: one persistent launch (Jacobi, or red-black SOR in the fusable sweep orders)
-			const int lp = p->no_bottom ? Lc : bottom_start(e);
+			const int lp = p->no_bottom ? Lc : bottom_start(e, s);
 			for (int l = 0; l < Lc - 1 && l < lp; ++l) {                                                    // :1531-1536
 				const bool zero = l > 0 || first;
 				if (FL(l)) TRY(fused_leg(e, l, s, p->v0, zero ? PRE_ZERO : PRE_GIVEN, POST_RESTRICT, B, U, W, 0));
@@ -2201,7 +2206,7 @@ static int pcmg_cycle(mgb_engine *e, const mgb_pcmg_params *p, int l, int bv, in
 	if (e->P > 1 && e->inkernel && l == e->La && l >= 1) TRY(wait_gather(e, l));
 	if (l >= 1 && !p->no_fuse && !p->no_bottom && p->coarse == MGB_COARSE_RICHARDSON && fusable(e, &p->level_smoother) &&
 	    fusable(e, &p->coarse_smoother) && p->level_smoother.type == p->coarse_smoother.type &&
-	    p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e) &&
+	    p->level_its >= 1 && p->coarse_its >= 1 && l == bottom_start(e, &p->level_smoother) &&
 	    bv == MGB_VEC_B && xv == MGB_VEC_U)
 		return bottom_cycle(e, l, &p->level_smoother, p->level_its, &p->coarse_smoother, p->coarse_its, true);
 	if (l == Lc - 1) {

@@ -2294,9 +2294,10 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 		// KSPSolve_CG, KSP_NORM_UNPRECONDITIONED (ref: src/solver.c:1922).  One iteration is ONE graph launch and ONE host
 		// read-back (||r||): beta = z'r, b = beta / betaold, dpi = p'w and a = beta / dpi are derived on the device where the
 		// dot products finish (k_reduce_tail, TAIL_*), the vector kernels read them from HBM.  The host sees all of them in
-		// the mapped mirror after the synchronisation and applies PETSc's tests in PETSc's order; the only difference to a
-		// host-driven loop is that on an indefinite-operator / indefinite-preconditioner exit x and r have already taken the
-		// update of that iteration.
+		// the mapped mirror after the synchronisation and applies PETSc's tests in PETSc's order.  On a beta == 0 /
+		// indefinite-preconditioner / indefinite-operator exit PETSc leaves before x is updated: with the deferred x update
+		// (k_cg_pstep) x is exactly PETSc's; only the internal work vector r has taken the update of that iteration (with
+		// MGB_CG_FUSE=0 x has taken it too).
 		double beta = 0.0, betaold = 1.0, dpi = 0.0, dpiold;
 		TRY(k_reduce(e, 0, R, -1, 0, 1)); TRY(read_scalars(e, 0, 1)); dp = hs[0];
 		logr(dp);
@@ -2341,16 +2342,18 @@ extern "C" int mgb_solve_pcmg(mgb_engine *e, const mgb_pcmg_params *p, double *r
 				ran = true;
 				betaold = beta; dpiold = dpi;
 				beta = hs[SC_BETA]; dpi = hs[SC_DPI]; dp = hs[0];
-				if (beta == 0.0) { reason = 3; break; }
-				else if (i > 0 && beta * betaold < 0.0) { reason = -8; break; }                    // KSP_DIVERGED_INDEFINITE_PC
-				if (dpi == 0.0 || (i > 0 && dpi * dpiold <= 0.0)) { reason = -10; break; }         // KSP_DIVERGED_INDEFINITE_MAT
+				// PETSc leaves these three exits BEFORE x takes the update of the iteration: with the deferred x update that is
+				// exactly what has happened here (the update of this iteration is still pending and is dropped)
+				if (beta == 0.0) { reason = 3; ran = false; break; }
+				else if (i > 0 && beta * betaold < 0.0) { reason = -8; ran = false; break; }       // KSP_DIVERGED_INDEFINITE_PC
+				if (dpi == 0.0 || (i > 0 && dpi * dpiold <= 0.0)) { reason = -10; ran = false; break; }   // KSP_DIVERGED_INDEFINITE_MAT
 				logr(dp);
 				reason = ksp_converged(p, i + 1, dp, &rnorm0, &ttol);
 				if (reason) break;
 				i++;
 			} while (i < p->max_iter);
 			if (i >= p->max_iter && !reason) reason = -3;                                          // KSP_DIVERGED_ITS
-			if (fuse_dir && ran) TRY(k_vecop<0>(e, 0, X, Pv, 0.0, SC_ALPHA));                      // the x += a p of the last iteration
+			if (fuse_dir && ran) TRY(k_vecop<0>(e, 0, X, Pv, 0.0, SC_ALPHA));                      // the pending x += a p of the last iteration
 		}
 	} else {
 		// KSPSolve_Richardson, general path (residual norm logged every iteration), scale 1

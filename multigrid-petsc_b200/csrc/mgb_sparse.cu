@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 extern "C" void mgb__set_error(const char *msg);     // mgb_engine.cu: the text behind mgb_last_error()
@@ -181,8 +182,10 @@ __global__ void k_sp_red2(const double *__restrict__ part, int nb, double *__res
 }
 // scratch of the reductions (block sums + the result), grown on demand and kept: a VecNorm per cycle must not cost a cudaMalloc
 static double *g_red_part = nullptr; static int g_red_cap = 0;
+static std::mutex g_red_mu;                              // the scratch is shared by every vector of the process
 static int reduce(int mode, const mgb_dvec *x, const mgb_dvec *y, double *out)
 {
+	std::lock_guard<std::mutex> lk(g_red_mu);
 	const int n = x->n, nb = (n + SP_RED_BLK - 1) / SP_RED_BLK;
 	if (n == 0) { *out = 0.0; return MGB_OK; }
 	if (nb + 1 > g_red_cap) {

@@ -386,6 +386,7 @@ static int create_body(mgb_engine *e, const mgb_config *cfg, int P, int dev)
 	{ const char *v = getenv("MGB_PDL"); if (v && v[0]) g_pdl = v[0] != '0'; }
 	{ const char *v = getenv("MGB_CG_FUSE"); if (v && v[0] == '0') e->cg_fuse = false; }
 	{ const char *v = getenv("MGB_RB_BOTTOM_ROWS"); if (v && v[0]) e->rb_coarse_threshold = atoi(v); }
+	{ const char *v = getenv("MGB_BOTTOM_ROWS"); if (v && v[0]) e->coarse_threshold = atoi(v); }
 	{ const char *v = getenv("MGB_RB_FUSE_MIN_ROWS"); if (v && v[0]) e->rb_fuse_min_rows = atoi(v); }
 	return MGB_OK;
 }

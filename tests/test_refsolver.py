@@ -178,7 +178,8 @@ def test_reference_solver_on_the_gpu_matches_its_cpu_run(name, tmp_path):
 
 @pytest.mark.gpu
 def test_reference_solver_really_ran_on_the_gpu(tmp_path):
-    """-moreNorm / KSPView prints the engine's launch counter: the arithmetic of the run above is CUDA kernels, not host loops"""
+    """the sparse C-ABI counts its kernel launches (mgb_sparse_launch_count, also printed by KSPView): vector and matrix
+    operations are CUDA kernels, not host loops -- create / set / norm launch at least three"""
     if not os.path.exists(BIN):
         pytest.skip("lib/poisson_petsc_b200 is not built")
     import ctypes as C
